@@ -1,0 +1,265 @@
+/*
+ * vgslm.h — C ABI of libvgslm.so, the B200 (sm_100a) kernel library behind the VAE-GSLM hot path.
+ *
+ * The reference (b04901014/vae-gslm) has no FFI layer of its own: its hot path is a graph of
+ * PyTorch nn.Modules.  Every entry point below therefore replaces the torch-library call sequence
+ * of ONE reference call site, cited as `file:line` (paths relative to the reference root).
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every buffer (inputs, outputs, saved-for-backward, workspace,
+ *     KV cache) is owned by the caller; nothing is allocated, freed or retained by the library;
+ *   - every function only ENQUEUES work on `stream` (no device/host synchronisation) and is
+ *     therefore CUDA-graph capturable;
+ *   - return value: 0 = ok, <0 = argument/shape/alignment error detected before launch,
+ *     >0 = cudaError_t.  `vg_last_error_string()` holds the message (thread-local);
+ *   - there is no CPU fallback: an unsupported shape is an error, never a silent dispatch;
+ *   - `dtype` arguments use vg_dtype; "act" tensors are the activation stream (f32 in parity mode,
+ *     bf16 in bf16 mode); statistics, losses and parameter gradients are always f32.
+ */
+#ifndef VGSLM_H_
+#define VGSLM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* vg_stream_t;
+
+typedef enum { VG_F32 = 0, VG_BF16 = 1 } vg_dtype;
+typedef enum { VG_ACT_NONE = 0, VG_ACT_RELU = 1, VG_ACT_GELU = 2 } vg_act;
+typedef enum { VG_GEMM_AUTO = 0, VG_GEMM_SIMT = 1, VG_GEMM_TCGEN05 = 2 } vg_gemm_backend;
+
+#define VG_VERSION 100
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         vg_version(void);
+const char* vg_last_error_string(void);
+/* 1 if the running device is compute capability 10.x (tcgen05/TMEM present), 0 otherwise, <0 error */
+int         vg_device_is_sm100(void);
+
+/* ---- RMSNorm: modules/norm.py:22-32 (+ the apply_mask that follows it, transformer/layers.py:53-54)
+ * y[r,:] = mask[r] ? scale * x[r,:] * rsqrt(mean(x[r,:]^2) + eps) : 0 ; rstd[r] saved for backward. */
+int vg_rmsnorm_fwd(const void* x, const float* scale, const uint8_t* row_mask /* nullable */,
+                   void* y, float* rstd, int64_t rows, int64_t dim, float eps,
+                   int x_dtype, int y_dtype, vg_stream_t stream);
+size_t vg_rmsnorm_bwd_workspace(int64_t rows, int64_t dim);
+/* dx = (dres ? dres : 0) + d/dx ; dscale[dim] overwritten (deterministic two-stage reduction). */
+int vg_rmsnorm_bwd(const void* dy, const void* x, const float* scale, const float* rstd,
+                   const uint8_t* row_mask /* nullable */, const void* dres /* nullable */,
+                   void* dx, float* dscale, void* workspace, size_t workspace_bytes,
+                   int64_t rows, int64_t dim, int x_dtype, int dy_dtype, vg_stream_t stream);
+
+/* ---- GEMM with fused epilogue: every nn.Linear on the path
+ * (attention.py:52,79; transformer/layers.py:82,152; lvtr.py:171,172,194,195; flow FiLM linear/layers.py:286)
+ *   acc = op(A)[M,K] · op(B)[K,N]
+ *   v   = acc + bias[n]                     (bias nullable)
+ *   if preact: preact[m,n] = v              (saved pre-activation, for GELU backward)
+ *   v   = act(v)
+ *   if dact_src: v *= act'(dact_src[m,n])   (dgrad epilogue: dact_src holds the saved pre-activation)
+ *   v  += residual[m,n]                     (nullable)
+ *   if row_mask && !row_mask[m]: v = 0      (TensorMask.apply_mask, utils/tensormask.py:63-67; with
+ *                                            mask_before_residual=1 the mask is applied BEFORE the
+ *                                            residual add: x + mask(y), transformer/layers.py:63)
+ *   C[m,n] = beta * C[m,n] + v              (beta in {0,1}; beta=1 needs f32 C: gradient accumulation)
+ * Storage: trans_a=0 → A is [M,K] row-major (ld = lda); trans_a=1 → A is stored [K,M] row-major.
+ *          trans_b=1 → B is stored [N,K] row-major (an nn.Linear weight); trans_b=0 → stored [K,N].
+ */
+typedef struct {
+  int64_t M, N, K;
+  const void* A; int64_t lda; int32_t trans_a;
+  const void* B; int64_t ldb; int32_t trans_b;
+  void* C; int64_t ldc;
+  int32_t ab_dtype;     /* vg_dtype of A and B */
+  int32_t c_dtype;      /* vg_dtype of C, preact, residual, dact_src */
+  const float* bias;
+  int32_t act;          /* vg_act applied after bias */
+  int32_t dact;         /* vg_act whose derivative multiplies the result (with dact_src) */
+  void* preact; int64_t ld_preact;
+  const void* dact_src; int64_t ld_dact;
+  const void* residual; int64_t ld_res;
+  const uint8_t* row_mask;
+  int32_t mask_before_residual;
+  float beta;
+} vg_gemm_args;
+size_t vg_gemm_workspace(const vg_gemm_args* a, int backend);
+int    vg_gemm(const vg_gemm_args* a, int backend, void* workspace, size_t workspace_bytes,
+               vg_stream_t stream);
+/* column sums: out[n] = sum_m X[m,n] (bias gradients), deterministic. */
+size_t vg_colsum_workspace(int64_t rows, int64_t cols);
+int    vg_colsum(const void* x, int64_t ld, float* out, int64_t rows, int64_t cols, int x_dtype,
+                 void* workspace, size_t workspace_bytes, vg_stream_t stream);
+
+/* ---- small elementwise helpers used by the backward passes
+ * vg_mask_rows: y[m,:] = mask[m] ? x[m,:] : 0           (backward of apply_mask; in-place allowed)
+ * vg_act_bwd  : dx = dy * act'(src) where src is the saved pre-activation (GELU) or the output (ReLU) */
+int vg_mask_rows(const void* x, const uint8_t* row_mask, void* y, int64_t rows, int64_t cols, int dtype,
+                 vg_stream_t stream);
+int vg_act_bwd(const void* dy, const void* src, void* dx, int64_t n, int act, int dtype, vg_stream_t stream);
+
+/* ---- causal self-attention with in-kernel ALiBi and per-sequence kv length:
+ * attention.py:52-78 (mask build + F.scaled_dot_product_attention) and position/alibi.py:6-33.
+ * q,k,v: [B, T*, H*D] views with row stride ld_q / ld_kv (elements) so they may alias a packed qkv
+ * buffer; query row iq sits at absolute position q_offset + iq (q_offset = Tk - Tq with a KV cache).
+ * score[b,h,i,j] = scale * q_i·k_j - slopes[h] * (i - j)   for j <= i and j < kv_len[b], else -inf.
+ * Rows with iq >= q_len[b] (padded queries) are written as zeros (the reference masks them after
+ * out_proj, attention.py:80).  lse[B,H,Tq] is saved for backward.                                   */
+int vg_attn_fwd(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv,
+                void* out, int64_t ld_out, float* lse,
+                const int32_t* kv_len /* [B] nullable */, const float* slopes /* [H] nullable */,
+                int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D, int64_t q_offset,
+                float scale, int dtype, vg_stream_t stream);
+size_t vg_attn_bwd_workspace(int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D);
+int vg_attn_bwd(const void* dout, int64_t ld_dout,
+                const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv,
+                const void* out, int64_t ld_out, const float* lse,
+                void* dq, void* dk, void* dv, int64_t ld_dq, int64_t ld_dkv,
+                const int32_t* kv_len, const float* slopes,
+                int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D, int64_t q_offset,
+                float scale, int dtype, void* workspace, size_t workspace_bytes, vg_stream_t stream);
+
+/* ---- KV-cache decode attention (single query per sequence): attention.py:56-85 in the cached
+ * LVTR.step loop (lvtr.py:253-257).  Cache layout: k_cache/v_cache [B, H, Tmax, D] (head-major).
+ * The new token's k/v (read from the packed qkv row of this step) are appended at index `pos`
+ * and attended together with cache rows [0,pos).                                                  */
+size_t vg_attn_decode_workspace(int64_t B, int64_t H, int64_t D, int64_t splits);
+int vg_attn_decode(const void* qkv /* [B, 3*H*D] */, void* k_cache, void* v_cache,
+                   void* out /* [B, H*D] */, const float* slopes,
+                   int64_t B, int64_t H, int64_t D, int64_t Tmax, int64_t pos,
+                   const int32_t* pos_dev /* nullable: device-resident position (CUDA-graph replay) */,
+                   int64_t splits, float scale, int dtype, void* workspace, size_t workspace_bytes,
+                   vg_stream_t stream);
+/* *counter += delta (device-side step counter used with pos_dev) */
+int vg_add_i32(int32_t* counter, int32_t delta, vg_stream_t stream);
+/* bulk append of a prefill chunk: k,v rows [B, T, H*D] (stride ld) → cache[:, :, pos:pos+T, :] */
+int vg_kv_append(const void* k, const void* v, int64_t ld, void* k_cache, void* v_cache,
+                 int64_t B, int64_t H, int64_t D, int64_t T, int64_t Tmax, int64_t pos, int dtype,
+                 vg_stream_t stream);
+
+/* ---- fused latent front end: lvtr.py:151-169 (+ linear/layers.py:87-134,150-152, lvtr.py:390-392)
+ * per frame: mean/logstd heads (Linear L→L), z = (mean + exp(logstd)·eps·temperature)·mask,
+ * log_q = (−logstd − 0.5 − 0.5 ln 2π)·mask, u = tok_emb[id]·mask + ReLU(Wf z + bf),
+ * u_shift[b,0] = s0[b]; u_shift[b,t] = u[b,t−1]; masked to the original lengths.                  */
+typedef struct {
+  int64_t B, T;
+  int32_t latent_dim;       /* L (4) */
+  int32_t emb_dim;          /* E (64) */
+  int32_t vocab;
+  const float* h_enc;       /* [B,T,L] encoder output */
+  const float* eps;         /* [B,T,L] caller-supplied N(0,1) */
+  const int64_t* ids;       /* [B,T] */
+  const uint8_t* mask;      /* [B,T] 1 = valid */
+  const float* init_state;  /* [B,E] (s0), nullable → zeros */
+  const float* w_mean; const float* b_mean;       /* [L,L],[L] */
+  const float* w_logstd; const float* b_logstd;   /* [L,L],[L] */
+  const float* tok_emb;     /* [vocab,E] */
+  const float* w_fuse; const float* b_fuse;       /* [E,L],[E] */
+  float temperature;
+  float* mean; float* logstd; float* z; float* log_q;    /* [B,T,L] outputs (f32) */
+  void* u; void* u_shift;   /* [B,T,E] act dtype */
+  int32_t act_dtype;
+} vg_latent_front_args;
+int vg_latent_front_fwd(const vg_latent_front_args* a, vg_stream_t stream);
+
+typedef struct {
+  vg_latent_front_args f;   /* forward arguments (inputs + saved outputs) */
+  const float* d_z;         /* [B,T,L] gradient reaching z from the flow (nullable) */
+  const float* d_log_q;     /* [B,T,L] nullable */
+  const float* d_mean_out;  /* [B,T,L] gradient on the exposed mean (nullable) */
+  const float* d_logstd_out;/* [B,T,L] nullable */
+  const void* d_u;          /* [B,T,E] act dtype, nullable */
+  const void* d_u_shift;    /* [B,T,E] act dtype, nullable */
+  float* d_h_enc;           /* [B,T,L] */
+  float* d_w_mean; float* d_b_mean; float* d_w_logstd; float* d_b_logstd;
+  float* d_tok_emb; float* d_w_fuse; float* d_b_fuse;     /* overwritten */
+} vg_latent_front_bwd_args;
+size_t vg_latent_front_bwd_workspace(int64_t B, int64_t T, int32_t L, int32_t E, int32_t vocab);
+int vg_latent_front_bwd(const vg_latent_front_bwd_args* a, void* workspace, size_t workspace_bytes,
+                        vg_stream_t stream);
+
+/* ---- fused latent back end: prior head consumption + conditional coupling flow + log_p + KL:
+ * lvtr.py:172-191, flow/layers.py:42-73,225-234, linear/layers.py:278-288, trainers/speech/lvtr.py:122-124.
+ * `head` is the [M, head_ld] f32 output of ONE GEMM whose columns are
+ *   [0,L) prior mean, [L,2L) prior logstd, then per flow layer l: 2*Hd FiLM columns (gamma | beta).
+ * Outputs log_p [M,L] (masked), y (flow output) and per-frame kl = mean_c(log_q − log_p);
+ * kl_sum[0] = Σ_valid kl (deterministic).                                                          */
+typedef struct {
+  int64_t M;                /* B*T frames */
+  int32_t latent_dim;       /* L = 4 (flow splits L/2 | L/2) */
+  int32_t hidden;           /* Hd = 64 */
+  int32_t n_layers;         /* 4 */
+  const float* head; int64_t head_ld;
+  const float* z;           /* [M,L] masked posterior sample */
+  const float* log_q;       /* [M,L] */
+  const uint8_t* mask;      /* [M] */
+  /* flow parameters, layer-major contiguous: w1 [n,Hd,L/2], b1 [n,Hd], ln_w [n,Hd], ln_b [n,Hd],
+   * w2 [n,L,Hd], b2 [n,L] */
+  const float* w1; const float* b1; const float* ln_w; const float* ln_b;
+  const float* w2; const float* b2;
+  float ln_eps; float scale_lo; float scale_hi;  /* σ-range: logs = ln(sigmoid(s)*(lo−hi)+hi) */
+  float* log_p;             /* [M,L] */
+  float* y;                 /* [M,L] flow output */
+  float* kl_frame;          /* [M] */
+  float* kl_sum;            /* [1] */
+} vg_latent_back_args;
+size_t vg_latent_back_workspace(int64_t M, int32_t L, int32_t Hd, int32_t n_layers);
+int vg_latent_back_fwd(const vg_latent_back_args* a, void* workspace, size_t workspace_bytes,
+                       vg_stream_t stream);
+typedef struct {
+  vg_latent_back_args f;
+  const float* d_log_p;     /* [M,L] upstream gradient on log_p */
+  float* d_head;            /* [M, head_ld] */
+  float* d_z;               /* [M,L] */
+  float* d_w1; float* d_b1; float* d_ln_w; float* d_ln_b; float* d_w2; float* d_b2; /* overwritten */
+} vg_latent_back_bwd_args;
+int vg_latent_back_bwd(const vg_latent_back_bwd_args* a, void* workspace, size_t workspace_bytes,
+                       vg_stream_t stream);
+/* decode-time inverse flow + prior sample: lvtr.py:267-275, flow/layers.py:75-99,236-245.
+ * z0 = mean_p + exp(logstd_p)·eps·temperature ; z = Flow^{-1}(z0; FiLM columns of head). */
+int vg_latent_prior_sample(const vg_latent_back_args* a, const float* eps, float temperature,
+                           float* z_out, vg_stream_t stream);
+
+/* ---- token cross-entropy: losses.py:30-41 (F.cross_entropy, ignore_index −100, reduction=sum)   */
+size_t vg_softmax_ce_workspace(int64_t rows);
+int vg_softmax_ce_fwd(const void* logits, int64_t ld, const int64_t* targets,
+                      const uint8_t* row_mask /* nullable; masked rows are ignored */,
+                      float* lse, float* loss_rows, float* loss_sum,
+                      int64_t rows, int64_t vocab, int dtype,
+                      void* workspace, size_t workspace_bytes, vg_stream_t stream);
+int vg_softmax_ce_bwd(const void* logits, int64_t ld, const int64_t* targets,
+                      const uint8_t* row_mask, const float* lse, const float* d_loss /* [1] device */,
+                      void* d_logits, int64_t ld_d, int64_t rows, int64_t vocab, int dtype,
+                      vg_stream_t stream);
+
+/* ---- diffusion loss glue: ddpm.py:328-334 (q_sample), 345-366 + losses.py:9-27,44-57 (masked L1) */
+int vg_qsample(const float* x0, const float* noise, const int64_t* t /* [B] */,
+               const float* sqrt_ac /* [steps] */, const float* sqrt_1mac, const uint8_t* mask,
+               float x0_scale, float* x_t, float* target, int64_t B, int64_t T, int64_t C,
+               vg_stream_t stream);
+size_t vg_masked_l1_workspace(int64_t B, int64_t T, int64_t C);
+int vg_masked_l1_fwd(const float* pred, const float* target, const uint8_t* mask, float* loss_sum,
+                     int64_t B, int64_t T, int64_t C, void* workspace, size_t workspace_bytes,
+                     vg_stream_t stream);
+int vg_masked_l1_bwd(const float* pred, const float* target, const uint8_t* mask,
+                     const float* d_loss, float* d_pred, int64_t B, int64_t T, int64_t C,
+                     vg_stream_t stream);
+
+/* ---- token sampling: lvtr.py:277-285 (softmax(logits/τ) → multinomial), plus a greedy mode
+ * (argmax; lowest index wins ties) used for bit-exact parity.  `u` = caller-supplied U[0,1) [rows].  */
+int vg_sample_token(const void* logits, int64_t ld, const float* u /* nullable → greedy */,
+                    float temperature, int64_t* out_ids, int64_t rows, int64_t vocab, int dtype,
+                    vg_stream_t stream);
+
+/* ---- optimizer: training_lib/optimizer.py:18-25,110-130 (AdamW) fused with the bf16 shadow cast  */
+int vg_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                  void* shadow_bf16 /* nullable */, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float bias_corr1, float bias_corr2,
+                  float grad_scale, vg_stream_t stream);
+int vg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGSLM_H_ */

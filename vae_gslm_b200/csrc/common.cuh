@@ -1,0 +1,120 @@
+// common.cuh — shared helpers for libvgslm (sm_100a).  Internal; the public ABI is include/vgslm.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/vgslm.h"
+
+namespace vg {
+
+void set_error(const char* fmt, ...);
+
+#define VG_REQUIRE(cond, code, ...)                     \
+  do {                                                  \
+    if (!(cond)) {                                      \
+      ::vg::set_error(__VA_ARGS__);                     \
+      return (code);                                    \
+    }                                                   \
+  } while (0)
+
+#define VG_LAUNCH_CHECK(name)                                                  \
+  do {                                                                         \
+    cudaError_t _e = cudaGetLastError();                                       \
+    if (_e != cudaSuccess) {                                                   \
+      ::vg::set_error("%s: launch failed: %s", name, cudaGetErrorString(_e));  \
+      return (int)_e;                                                          \
+    }                                                                          \
+  } while (0)
+
+#define VG_CUDA(call)                                                             \
+  do {                                                                            \
+    cudaError_t _e = (call);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      ::vg::set_error("%s failed: %s", #call, cudaGetErrorString(_e));            \
+      return (int)_e;                                                             \
+    }                                                                             \
+  } while (0)
+
+static inline bool valid_dtype(int d) { return d == VG_F32 || d == VG_BF16; }
+static inline size_t dtype_size(int d) { return d == VG_F32 ? 4 : 2; }
+static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- device helpers ---------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// exact (erf) GELU, torch.nn.GELU() default — modules/activations.py:11
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == VG_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == VG_ACT_GELU) return gelu_f(v);
+  return v;
+}
+__device__ __forceinline__ float act_grad(float pre, int act) {
+  if (act == VG_ACT_RELU) return pre > 0.f ? 1.f : 0.f;
+  if (act == VG_ACT_GELU) return gelu_grad_f(pre);
+  return 1.f;
+}
+
+// 8-wide vector of activation values, loaded/stored as one 16 B (bf16) or two 16 B (f32) accesses.
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  float v[8];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = raw;
+  }
+};
+
+}  // namespace vg
