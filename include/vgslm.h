@@ -102,7 +102,9 @@ int vg_act_bwd(const void* dy, const void* src, void* dx, int64_t n, int act, in
 /* ---- causal self-attention with in-kernel ALiBi and per-sequence kv length:
  * attention.py:52-78 (mask build + F.scaled_dot_product_attention) and position/alibi.py:6-33.
  * q,k,v: [B, T*, H*D] views with row stride ld_q / ld_kv (elements) so they may alias a packed qkv
- * buffer; query row iq sits at absolute position q_offset + iq (q_offset = Tk - Tq with a KV cache).
+ * buffer; K/V may instead be a head-major cache [B,H,Tmax,D] (ld_kv = D, kv_head_stride = Tmax*D,
+ * kv_batch_stride = H*Tmax*D).  Query row iq sits at absolute position q_offset + iq
+ * (q_offset = Tk - Tq with a KV cache).
  * score[b,h,i,j] = scale * q_i·k_j - slopes[h] * (i - j)   for j <= i and j < kv_len[b], else -inf.
  * Rows with iq >= q_len[b] (padded queries) are written as zeros (the reference masks them after
  * out_proj, attention.py:80).  lse[B,H,Tq] is saved for backward.                                   */
@@ -110,6 +112,7 @@ int vg_attn_fwd(const void* q, const void* k, const void* v, int64_t ld_q, int64
                 void* out, int64_t ld_out, float* lse,
                 const int32_t* kv_len /* [B] nullable */, const float* slopes /* [H] nullable */,
                 int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D, int64_t q_offset,
+                int64_t kv_batch_stride /* 0 → Tk*ld_kv (packed) */, int64_t kv_head_stride /* 0 → D */,
                 float scale, int dtype, vg_stream_t stream);
 size_t vg_attn_bwd_workspace(int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D);
 int vg_attn_bwd(const void* dout, int64_t ld_dout,

@@ -1,0 +1,287 @@
+"""Per-kernel parity of libvgslm (through ops / the C ABI) against plain PyTorch on the same GPU.
+Tolerances: fp32 kernels 1e-4 relative (north star), bf16 kernels 2e-2."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from vae_gslm_b200 import _lib as L          # noqa: E402
+from vae_gslm_b200 import ops                # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def tol(dtype):
+    return 2e-2 if dtype == torch.bfloat16 else 1e-4
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(1234)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def test_library_reports_device():
+    assert L.load().vg_version() == 100
+    assert L.load().vg_device_is_sm100() == 1, "these kernels are built for sm_100a (B200)"
+
+
+def test_cpu_tensor_is_refused():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.rmsnorm(torch.randn(4, 64), torch.ones(64), 1e-6)
+
+
+# ------------------------------------------------------------------------------------ rmsnorm
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,dim,masked", [(37, 1024, True), (5, 64, False), (513, 256, True), (8, 2048, False)])
+def test_rmsnorm_fwd_bwd(dtype, rows, dim, masked):
+    x = torch.randn(rows, dim, device=DEV).to(dtype).requires_grad_(True)
+    scale = (1 + 0.1 * torch.randn(dim, device=DEV)).requires_grad_(True)
+    mask = (torch.rand(rows, device=DEV) > 0.3) if masked else None
+    y = ops.rmsnorm(x, scale, 1e-6, mask)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    sr = scale.detach().clone().requires_grad_(True)
+    yr = sr * (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6))
+    if masked:
+        yr = torch.where(mask[:, None], yr, 0.0)
+    yr.backward(gy.float())
+    assert rel_err(y, yr) < tol(dtype)
+    assert rel_err(x.grad, xr.grad) < tol(dtype)
+    assert rel_err(scale.grad, sr.grad) < tol(dtype)
+
+
+# ------------------------------------------------------------------------------------ GEMM (SIMT)
+def _gemm_ref(a, b, trans_a, trans_b):
+    A = a.float().t() if trans_a else a.float()
+    B = b.float().t() if trans_b else b.float()
+    return A @ B
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("trans_a,trans_b", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(70, 50, 33), (128, 200, 64), (5, 8, 4)])
+def test_gemm_simt_layouts(dtype, trans_a, trans_b, M, N, K):
+    a = torch.randn((K, M) if trans_a else (M, K), device=DEV).to(dtype)
+    b = torch.randn((N, K) if trans_b else (K, N), device=DEV).to(dtype)
+    out = ops.gemm(a, b, trans_a=trans_a, trans_b=trans_b, out_dtype=torch.float32, backend=ops.GEMM_SIMT)
+    assert rel_err(out, _gemm_ref(a, b, trans_a, trans_b)) < 1e-5
+
+
+@pytest.mark.parametrize("backend", ["simt", "tcgen05"])
+def test_gemm_epilogue(backend):
+    be = ops.GEMM_SIMT if backend == "simt" else ops.GEMM_TCGEN05
+    dtype = torch.bfloat16
+    M, N, K = 200, 264, 128
+    a = torch.randn(M, K, device=DEV).to(dtype)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(dtype)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV).to(dtype)
+    mask = torch.rand(M, device=DEV) > 0.25
+    pre = torch.empty(M, N, device=DEV, dtype=dtype)
+    acc = a.float() @ w.float().t() + bias
+    # bias + GELU + stored pre-activation
+    out = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, preact=pre, backend=be)
+    assert rel_err(pre, acc) < 2e-2 and rel_err(out, torch.nn.functional.gelu(acc)) < 2e-2
+    # bias + residual, mask after / before the residual
+    out = ops.gemm(a, w, bias=bias, residual=res, row_mask=ops._u8(mask), backend=be)
+    assert rel_err(out, torch.where(mask[:, None], acc + res.float(), 0.0)) < 2e-2
+    out = ops.gemm(a, w, bias=bias, residual=res, row_mask=ops._u8(mask), mask_first=True, backend=be)
+    assert rel_err(out, torch.where(mask[:, None], acc, 0.0) + res.float()) < 2e-2
+    # dgrad epilogue: multiply by GELU'(saved pre-activation)
+    out = ops.gemm(a, w, dact_src=pre, dact=ops.ACT_GELU, backend=be)
+    p = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(p).sum().backward()
+    assert rel_err(out, (a.float() @ w.float().t()) * p.grad) < 2e-2
+    # f32 accumulate (beta = 1)
+    c = torch.randn(M, N, device=DEV)
+    ref = c + a.float() @ w.float().t()
+    ops.gemm(a, w, out=c, beta=1.0, backend=be)
+    assert rel_err(c, ref) < 1e-2
+
+
+# ------------------------------------------------------------------------------------ GEMM (tcgen05)
+@pytest.mark.parametrize("trans_a,trans_b", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (640, 1024, 1024), (333, 200, 192),
+                                   (5120, 3072, 1024), (130, 520, 1024), (1024, 64, 1024), (64, 1024, 5000)])
+def test_gemm_tcgen05_layouts(trans_a, trans_b, M, N, K):
+    Mp, Np, Kp = (M + 7) // 8 * 8, (N + 7) // 8 * 8, (K + 7) // 8 * 8     # leading dims must be multiples of 8
+    a_full = torch.randn((Kp, Mp) if trans_a else (Mp, Kp), device=DEV).to(torch.bfloat16)
+    b_full = torch.randn((Np, Kp) if trans_b else (Kp, Np), device=DEV).to(torch.bfloat16)
+    a = a_full[:K, :M] if trans_a else a_full[:M, :K]
+    b = b_full[:N, :K] if trans_b else b_full[:K, :N]
+    out = ops.gemm(a, b, trans_a=trans_a, trans_b=trans_b, out_dtype=torch.float32, backend=ops.GEMM_TCGEN05)
+    ref = _gemm_ref(a, b, trans_a, trans_b)
+    assert rel_err(out, ref) < 2e-3, f"tcgen05 GEMM mismatch {rel_err(out, ref)}"
+    out16 = ops.gemm(a, b, trans_a=trans_a, trans_b=trans_b, backend=ops.GEMM_TCGEN05)
+    assert rel_err(out16, ref) < 1e-2
+
+
+def test_colsum():
+    x = torch.randn(1000, 520, device=DEV)
+    assert rel_err(ops.colsum(x), x.sum(0)) < 1e-5
+    xb = x.to(torch.bfloat16)
+    assert rel_err(ops.colsum(xb), xb.float().sum(0)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, H, lengths, slopes, q_offset=0, k=None, v=None):
+    B, Tq, C3 = qkv.shape
+    C = C3 // 3
+    D = C // H
+    q = qkv[..., :C].float()
+    k = qkv[..., C:2 * C].float() if k is None else k.float()
+    v = qkv[..., 2 * C:].float() if v is None else v.float()
+    Tk = k.shape[1]
+    qh, kh, vh = (t.reshape(B, t.shape[1], H, D).transpose(1, 2) for t in (q, k, v))
+    i = torch.arange(q_offset, q_offset + Tq, device=qkv.device)[:, None]
+    j = torch.arange(Tk, device=qkv.device)[None, :]
+    ok = (j <= i)[None, None]
+    if lengths is not None:
+        ok = ok & (j[None, None] < lengths.view(B, 1, 1, 1))
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(D)
+    if slopes is not None:
+        s = s - slopes.view(1, H, 1, 1) * (i - j).clamp(min=0)[None, None]
+    w = torch.softmax(s.masked_fill(~ok, float("-inf")), -1)
+    o = (w @ vh).transpose(1, 2).reshape(B, Tq, C)
+    if lengths is not None:   # padded query rows are written as zeros by the kernel
+        valid_q = (i.view(1, Tq) < lengths.view(B, 1))
+        o = torch.where(valid_q[..., None], o, 0.0)
+    return o
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,H", [(2, 24, 2), (3, 130, 4), (2, 640, 16)])
+def test_attention_fwd_bwd(dtype, B, T, H):
+    D = 64
+    qkv = (0.5 * torch.randn(B, T, 3 * H * D, device=DEV)).to(dtype).requires_grad_(True)
+    lengths = torch.randint(T // 2, T + 1, (B,), device=DEV, dtype=torch.int32)
+    lengths[0] = T
+    slopes = torch.tensor(ops.alibi_slopes(H), device=DEV)
+    o = ops.attention(qkv, H, lengths, slopes)
+    go = torch.randn_like(o)
+    valid = torch.arange(T, device=DEV)[None, :] < lengths[:, None]
+    go = torch.where(valid[..., None], go, torch.zeros_like(go))     # upstream of padded rows is masked in the model
+    o.backward(go)
+    qr = qkv.detach().float().requires_grad_(True)
+    orf = _attn_ref(qr, H, lengths, slopes)
+    orf.backward(go.float())
+    assert rel_err(o, orf) < tol(dtype)
+    # gradients of padded positions are exactly zero in both
+    assert rel_err(qkv.grad, qr.grad) < (4e-2 if dtype == torch.bfloat16 else 2e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_decode_and_cache(dtype):
+    B, H, D, Tmax = 3, 4, 64, 96
+    C = H * D
+    slopes = torch.tensor(ops.alibi_slopes(H), device=DEV)
+    kc = torch.zeros(B, H, Tmax, D, device=DEV, dtype=dtype)
+    vc = torch.zeros_like(kc)
+    # prefill 17 positions through kv_append + packed attention, then 5 single-token steps
+    qkv0 = (0.5 * torch.randn(B, 17, 3 * C, device=DEV)).to(dtype)
+    ops.kv_append(qkv0[..., C:2 * C], qkv0[..., 2 * C:], kc, vc, 0)
+    o0 = ops.attention_cached(qkv0[..., :C], qkv0[..., C:2 * C], qkv0[..., 2 * C:], H, 0, slopes)
+    assert rel_err(o0, _attn_ref(qkv0, H, None, slopes)) < tol(dtype)
+    k_all, v_all = qkv0[..., C:2 * C].clone(), qkv0[..., 2 * C:].clone()
+    pos = 17
+    for step in range(5):
+        qkv = (0.5 * torch.randn(B, 1, 3 * C, device=DEV)).to(dtype)
+        for splits in (1, 3):
+            kc2, vc2 = kc.clone(), vc.clone()
+            o = ops.attention_decode(qkv.view(B, 3 * C), kc2, vc2, pos, slopes, splits=splits)
+            k_ref = torch.cat([k_all, qkv[..., C:2 * C]], 1)
+            v_ref = torch.cat([v_all, qkv[..., 2 * C:]], 1)
+            ref = _attn_ref(qkv, H, None, slopes, q_offset=pos, k=k_ref, v=v_ref)
+            assert rel_err(o.view(B, 1, C), ref) < tol(dtype), (step, splits)
+        kc, vc, k_all, v_all = kc2, vc2, k_ref, v_ref
+        pos += 1
+    # the cache holds exactly what was appended, head-major
+    got = kc[:, :, :pos].transpose(1, 2).reshape(B, pos, C)
+    assert torch.equal(got, k_all)
+    # multi-token chunk against the head-major cache (prefill with a past)
+    qkv = (0.5 * torch.randn(B, 7, 3 * C, device=DEV)).to(dtype)
+    ops.kv_append(qkv[..., C:2 * C], qkv[..., 2 * C:], kc, vc, pos)
+    o = ops.attention_cached(qkv[..., :C], kc, vc, H, pos, slopes, head_major=True, tk=pos + 7)
+    ref = _attn_ref(qkv, H, None, slopes, q_offset=pos, k=torch.cat([k_all, qkv[..., C:2 * C]], 1),
+                    v=torch.cat([v_all, qkv[..., 2 * C:]], 1))
+    assert rel_err(o, ref) < tol(dtype)
+
+
+# ------------------------------------------------------------------------------------ losses
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_softmax_ce(dtype):
+    rows, V = 333, 200
+    logits = (2 * torch.randn(rows, V, device=DEV)).to(dtype).requires_grad_(True)
+    tgt = torch.randint(0, V, (rows,), device=DEV)
+    mask = torch.rand(rows, device=DEV) > 0.2
+    loss = ops.softmax_ce(logits, tgt, mask)
+    (loss * 0.7).backward()
+    lr = logits.detach().float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr, torch.where(mask, tgt, -100), reduction="sum", ignore_index=-100)
+    (ref * 0.7).backward()
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < 1e-5
+    assert rel_err(logits.grad, lr.grad) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
+
+
+def test_qsample_and_masked_l1():
+    B, T, C = 3, 50, 80
+    x0, noise = torch.randn(B, T, C, device=DEV), torch.randn(B, T, C, device=DEV)
+    t = torch.randint(0, 1000, (B,), device=DEV)
+    sa, s1 = torch.rand(1000, device=DEV), torch.rand(1000, device=DEV)
+    mask = torch.arange(T, device=DEV)[None, :] < torch.tensor([50, 31, 7], device=DEV)[:, None]
+    x_t, target = ops.qsample(x0, noise, t, sa, s1, mask)
+    ref = torch.where(mask[..., None], sa[t].view(B, 1, 1) * x0 + s1[t].view(B, 1, 1) * noise, 0.0)
+    assert rel_err(x_t, ref) < 1e-6 and rel_err(target, torch.where(mask[..., None], noise, 0.0)) < 1e-6
+    pred = torch.randn(B, T, C, device=DEV, requires_grad=True)
+    loss = ops.masked_l1(pred, target, mask)
+    (loss * 1.3).backward()
+    pr = pred.detach().clone().requires_grad_(True)
+    lref = (torch.where(mask[..., None], pr, 0.0) - target).abs().mean(-1).sum()
+    (lref * 1.3).backward()
+    assert abs(float(loss) - float(lref)) / float(lref) < 1e-5
+    assert rel_err(pred.grad, pr.grad) < 1e-6
+
+
+def test_sample_token():
+    rows, V = 64, 200
+    logits = 3 * torch.randn(rows, V, device=DEV)
+    assert torch.equal(ops.sample_token(logits, None), logits.argmax(-1))
+    # inverse-CDF sampling: empirical frequencies follow softmax(logits / tau)
+    one = logits[:1].expand(20000, V).contiguous()
+    u = torch.rand(20000, device=DEV)
+    ids = ops.sample_token(one, u, 0.85)
+    freq = torch.bincount(ids, minlength=V).float() / 20000
+    p = torch.softmax(logits[0] / 0.85, -1)
+    assert float((freq - p).abs().max()) < 0.02
+    # exact check of the CDF rule
+    cdf = torch.cumsum(torch.softmax(one[:100] / 0.85, -1), -1)
+    expect = (cdf <= u[:100, None] * cdf[:, -1:]).sum(-1).clamp(max=V - 1)
+    assert (ids[:100] == expect).float().mean() > 0.97      # ties at float rounding boundaries aside
+
+
+def test_adamw_matches_torch():
+    n = 10007
+    p = torch.randn(n, device=DEV)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=5e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.1)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    arena = torch.empty(n + 16, device=DEV)[:n].copy_(p)
+    shadow = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    for step in range(1, 4):
+        g = torch.randn(n, device=DEV)
+        ref.grad = g.clone()
+        opt.step()
+        L.call("vg_adamw_step", L.ptr(arena), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(shadow), n, 5e-4, 0.9, 0.98, 1e-8,
+               0.1, 1 - 0.9 ** step, 1 - 0.98 ** step, 1.0, L.stream())
+    assert rel_err(arena, ref.detach()) < 1e-6
+    assert torch.equal(shadow, arena.to(torch.bfloat16))

@@ -1,0 +1,293 @@
+"""End-to-end parity of the CUDA path (vae_gslm_b200.models.speech.lvtr.LVTR, through the C ABI) against
+(a) the committed golden vectors produced by the real reference and (b) the oracle run on the same inputs.
+
+Tolerances are the north star's: 1e-4 relative in fp32 mode; 2e-2 relative on loss, logits and grads in
+bf16 mode; greedy token ids bit-exact in fp32."""
+import copy
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import lvtr_oracle as O                                     # noqa: E402  (checker only)
+from vae_gslm_b200 import ops                                           # noqa: E402
+from vae_gslm_b200.hparams.hp import Hparams                            # noqa: E402
+from vae_gslm_b200.models.speech.lvtr import LVTR                       # noqa: E402
+from vae_gslm_b200.trainers.speech.lvtr import assemble_loss            # noqa: E402
+from vae_gslm_b200.utils.tensormask import TensorMask                   # noqa: E402
+
+DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def frob_rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def max_rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-20))
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ops.GEMM_BACKEND = ops.GEMM_AUTO
+    yield
+    ops.GEMM_BACKEND = ops.GEMM_AUTO
+
+
+def build_small(golden, dtype=torch.float32):
+    model = LVTR(Hparams.from_dict(copy.deepcopy(golden["config"])), input_dim=golden["n_mels"])
+    missing, unexpected = model.load_state_dict(golden["state_dict"], strict=False)
+    assert not unexpected and all(k.startswith("decoder.") for k in missing), (missing, unexpected)
+    return model.to(DEV).set_compute_dtype(dtype)
+
+
+def run_forward(model, g, kw):
+    i = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in g["inputs"].items()}
+    out = model(TensorMask(i["x"], i["mask"]), utterance=TensorMask(i["utterance"], i["utt_mask"]),
+                eps_q=i["eps_q"], init_state=i["init_state"], eps_p=i["eps_p"], diff_t=i["diff_t"],
+                diff_noise=i["diff_noise"])
+    return out, assemble_loss(out, kld_weight=kw)
+
+
+def test_fp32_forward_backward_matches_reference(golden):
+    model = build_small(golden)
+    f = golden["forward"]
+    out, terms = run_forward(model, golden, float(f["kw"]))
+    model.zero_grad()
+    terms["loss"].backward()
+    T = 1e-4
+    assert abs(float(terms["rec_loss"]) - float(f["rec"])) / abs(float(f["rec"])) < T
+    assert abs(float(terms["kld"]) - float(f["kld"])) / abs(float(f["kld"])) < T
+    assert abs(float(terms["token_kld"]) - float(f["ce"])) / abs(float(f["ce"])) < T
+    assert abs(float(terms["loss"]) - float(f["loss"])) / abs(float(f["loss"])) < T
+    for mine, ref in ((out["log_p"].value, f["log_p"]), (out["log_q"].value, f["log_q"]),
+                      (out["transformer_latent"].value, f["transformer_latent"]), (out["logits"].value, f["logits"]),
+                      (out["sample_q"].value, f["sample_q"]), (out["u_c"], f["u_c"])):
+        assert max_rel(mine.cpu(), ref) < T
+    # masked_loss route (un-fused KL) agrees with the fused kl_sum
+    t2 = assemble_loss(out, kld_weight=float(f["kw"]), use_fused_kl=False)
+    assert abs(float(t2["kld"]) - float(terms["kld"])) / abs(float(f["kld"])) < 1e-5
+    # padded rows are exactly zero
+    pad = ~golden["inputs"]["mask"]
+    for k in ("transformer_latent", "log_p", "log_q", "sample_q"):
+        assert float(out[k].value.cpu()[pad].abs().max()) == 0.0, k
+    # every parameter receives a gradient matching the reference
+    worst = 0.0
+    for name, p in model.named_parameters():
+        assert p.grad is not None, name
+        worst = max(worst, max_rel(p.grad.cpu(), golden["grads"][name]))
+        assert max_rel(p.grad.cpu(), golden["grads"][name]) < 2e-4, name
+    print("worst fp32 grad rel err", worst)
+
+
+@pytest.mark.parametrize("backend", ["simt", "tcgen05"])
+def test_bf16_forward_backward_within_tolerance(golden, backend):
+    ops.GEMM_BACKEND = ops.GEMM_SIMT if backend == "simt" else ops.GEMM_AUTO
+    model = build_small(golden, torch.bfloat16)
+    f = golden["forward"]
+    out, terms = run_forward(model, golden, float(f["kw"]))
+    model.zero_grad()
+    terms["loss"].backward()
+    T = 2e-2
+    assert abs(float(terms["loss"]) - float(f["loss"])) / abs(float(f["loss"])) < T
+    assert abs(float(terms["token_kld"]) - float(f["ce"])) / abs(float(f["ce"])) < T
+    assert abs(float(terms["kld"]) - float(f["kld"])) / abs(float(f["kld"])) < T
+    assert max_rel(out["logits"].value.cpu(), f["logits"]) < T
+    bad = []
+    for name, p in model.named_parameters():
+        e = frob_rel(p.grad.cpu(), golden["grads"][name])
+        if e > 5e-2:
+            bad.append((name, e))
+    assert not bad, bad
+
+
+def test_fp32_cached_decode_greedy_tokens_bit_exact(golden):
+    model = build_small(golden).eval()
+    d = golden["decode"]
+    state, kv = d["prompt"].to(DEV), None
+    model.transformer[0].cache_len_hint = 32
+    for i, eps in enumerate(d["eps"]):
+        o = model.step(state, past_kv=kv, temperature=0.85, push_init_state=(i == 0), eps=eps.to(DEV), greedy=True,
+                       init_state=d["init_state"].to(DEV), return_logits=True)
+        assert max_rel(o["transformer_latent"].value.cpu(), d["latents"][i]) < 1e-4
+        assert max_rel(o["logits"].cpu(), d["logits"][i]) < 1e-4
+        assert torch.equal(o["output"][..., 0].cpu(), d["outputs"][i][..., 0]), "greedy token ids differ"
+        assert max_rel(o["output"][..., 1:].cpu(), d["outputs"][i][..., 1:]) < 1e-4
+        kv = o["kv"]
+        state = d["outputs"][i][:, -1:].to(DEV)          # teacher-force the reference's own output
+    assert max_rel(kv[0]["key"].cpu(), d["final_kv_key0"]) < 1e-4
+    # reference-style dict cache is accepted as past_kv too (compatibility path)
+    ref_kv = [{"key": h["key"].clone(), "value": h["value"].clone()} for h in kv]
+    o2 = model.step(state, past_kv=ref_kv, temperature=0.85, eps=d["eps"][-1].to(DEV), greedy=True)
+    assert o2["output"].shape == (state.shape[0], 1, 5)
+
+
+def test_bf16_cached_decode_close(golden):
+    model = build_small(golden, torch.bfloat16).eval()
+    d = golden["decode"]
+    state, kv = d["prompt"].to(DEV), None
+    for i, eps in enumerate(d["eps"]):
+        o = model.step(state, past_kv=kv, temperature=0.85, push_init_state=(i == 0), eps=eps.to(DEV), greedy=True,
+                       init_state=d["init_state"].to(DEV), return_logits=True)
+        assert max_rel(o["logits"].float().cpu(), d["logits"][i]) < 3e-2
+        kv = o["kv"]
+        state = d["outputs"][i][:, -1:].to(DEV)
+
+
+# ------------------------------------------------------------------------- fused latent kernels vs oracle
+def test_latent_kernels_against_oracle(golden):
+    sd = {k: v.to(DEV) for k, v in golden["state_dict"].items()}
+    cfg = golden["config"]
+    torch.manual_seed(5)
+    B, T, Ld, Dm = 3, 37, 4, cfg["transformer"]["layer"]["dim"]
+    mask = torch.arange(T, device=DEV)[None, :] < torch.tensor([37, 20, 1], device=DEV)[:, None]
+    # ---- back end: flow + log_p + KL, forward and backward
+    cvec = torch.randn(B, T, Dm, device=DEV, requires_grad=True)
+    z = torch.where(mask[..., None], torch.randn(B, T, Ld, device=DEV), 0.0).requires_grad_(True)
+    log_q = torch.where(mask[..., None], torch.randn(B, T, Ld, device=DEV), 0.0).requires_grad_(True)
+    fl = cfg["transformer"]["flow"]
+    names = [f"transformer_flow.layers.{i}" for i in range(fl["num_layers"])]
+    params = {n: sd[n].clone().requires_grad_(True) for n in sd if n.startswith(("transformer_flow.", "transformer.1."))}
+
+    def oracle_side(c_, z_, lq_, p_):
+        full = dict(sd)
+        full.update(p_)
+        mean_p = O._lin(full, "transformer.1.mean", c_)
+        logstd_p = O._lin(full, "transformer.1.logstd", c_)
+        y, logdet = O.flow_forward(full, "transformer_flow", fl, z_, mask, c_)
+        lp = (logdet.sum(-1) / Ld)[..., None] - logstd_p - O.HALF_LOG_2PI - 0.5 * torch.exp(-2 * logstd_p) * (y - mean_p) ** 2
+        lp = O._mask3(lp, mask)
+        return lp, (O._mask3(lq_, mask) - lp).mean(-1).sum()
+
+    lp_ref, kl_ref = oracle_side(cvec, z, log_q, params)
+    w_up = torch.randn_like(lp_ref)
+    (kl_ref * 0.04 + (lp_ref * w_up).sum()).backward()
+    ref_grads = {n: p.grad.clone() for n, p in params.items()}
+    ref_c, ref_z, ref_lq = cvec.grad.clone(), z.grad.clone(), log_q.grad.clone()
+
+    c2 = cvec.detach().clone().requires_grad_(True)
+    z2 = z.detach().clone().requires_grad_(True)
+    lq2 = log_q.detach().clone().requires_grad_(True)
+    p2 = {n: p.detach().clone().requires_grad_(True) for n, p in params.items()}
+    head_w = torch.cat([p2["transformer.1.mean.weight"], p2["transformer.1.logstd.weight"]] +
+                       [p2[n + ".film.linear.weight"] for n in names], 0)
+    head_b = torch.cat([p2["transformer.1.mean.bias"], p2["transformer.1.logstd.bias"]] +
+                       [p2[n + ".film.linear.bias"] for n in names], 0)
+    head = ops.linear(c2, head_w, head_b, out_dtype=torch.float32)
+    stacked = [torch.stack([p2[f"{n}.{k}"] for n in names]) for k in
+               ("linear1.weight", "linear1.bias", "norm.weight", "norm.bias", "linear2.weight", "linear2.bias")]
+    lp, y, kl = ops.latent_back(head, z2, lq2, mask, *stacked, fl["layer"]["norm"]["eps"], 0.5, 2.0)
+    (kl * 0.04 + (lp * w_up).sum()).backward()
+    assert max_rel(lp, lp_ref) < 1e-4 and abs(float(kl) - float(kl_ref)) / abs(float(kl_ref)) < 1e-4
+    assert max_rel(c2.grad, ref_c) < 2e-4 and max_rel(z2.grad, ref_z) < 2e-4 and max_rel(lq2.grad, ref_lq) < 1e-5
+    for n in params:
+        assert max_rel(p2[n].grad, ref_grads[n]) < 2e-4, n
+
+    # ---- inverse flow (decode) inverts the forward flow
+    with torch.no_grad():
+        eps = torch.randn(B, T, Ld, device=DEV)
+        z_dec = ops.latent_prior_sample(head.detach(), eps, 0.85, *[s.detach() for s in stacked],
+                                        fl["layer"]["norm"]["eps"], 0.5, 2.0)
+        cc = torch.relu(cvec.detach()) * 0 + cvec.detach()
+        mean_p, logstd_p = O._lin(sd, "transformer.1.mean", cc), O._lin(sd, "transformer.1.logstd", cc)
+        z_ref = O.flow_reverse(sd, "transformer_flow", fl, mean_p + eps * torch.exp(logstd_p) * 0.85, cc)
+        assert max_rel(z_dec, z_ref) < 1e-4
+
+    # ---- front end: posterior heads + reparam + log_q + embedding + fuse + shift, forward and backward
+    E, V = 64, cfg["tokens"]["vocab_size"]
+    h_enc = torch.randn(B, T, Ld, device=DEV, requires_grad=True)
+    eps_q = torch.randn(B, T, Ld, device=DEV)
+    ids = torch.randint(0, V, (B, T), device=DEV)
+    s0 = torch.rand(B, 1, E, device=DEV) * 2 - 1
+    fp = {n: sd[n].clone().requires_grad_(True) for n in ("encoder.1.mean.weight", "encoder.1.mean.bias",
+          "encoder.1.logstd.weight", "encoder.1.logstd.bias", "token_embedding.weight", "token_fuser.linear.weight",
+          "token_fuser.linear.bias")}
+
+    def front_ref(h_, p_):
+        mean = torch.nn.functional.linear(h_, p_["encoder.1.mean.weight"], p_["encoder.1.mean.bias"])
+        logstd = torch.nn.functional.linear(h_, p_["encoder.1.logstd.weight"], p_["encoder.1.logstd.bias"])
+        zz = O._mask3(mean + eps_q * torch.exp(logstd), mask)
+        lq = O._mask3(-logstd - 0.5 - O.HALF_LOG_2PI, mask)
+        emb = O._mask3(torch.nn.functional.embedding(ids, p_["token_embedding.weight"]), mask)
+        u = emb + torch.relu(torch.nn.functional.linear(zz, p_["token_fuser.linear.weight"], p_["token_fuser.linear.bias"]))
+        us = O._mask3(torch.cat([s0, u], 1)[:, :-1], mask)
+        return mean, logstd, zz, lq, u, us
+
+    outs_ref = front_ref(h_enc, fp)
+    ws = [torch.randn_like(o) for o in outs_ref]
+    sum((o * w).sum() for o, w in zip(outs_ref, ws)).backward()
+    h2 = h_enc.detach().clone().requires_grad_(True)
+    fp2 = {n: p.detach().clone().requires_grad_(True) for n, p in fp.items()}
+    outs = ops.latent_front(h2, eps_q, ids, mask, s0.reshape(B, E), fp2["encoder.1.mean.weight"],
+                            fp2["encoder.1.mean.bias"], fp2["encoder.1.logstd.weight"], fp2["encoder.1.logstd.bias"],
+                            fp2["token_embedding.weight"], fp2["token_fuser.linear.weight"],
+                            fp2["token_fuser.linear.bias"], 1.0, torch.float32)
+    for o, r in zip(outs, outs_ref):
+        assert max_rel(o, r) < 1e-5
+    sum((o * w).sum() for o, w in zip(outs, ws)).backward()
+    assert max_rel(h2.grad, h_enc.grad) < 1e-4
+    for n in fp:
+        assert max_rel(fp2[n].grad, fp[n].grad) < 1e-4, n
+
+
+# ------------------------------------------------------------------------- full-size configuration vs the oracle
+def _full_model_and_batch(B, T, seed=0):
+    from vae_gslm_b200.training_lib.trainer import init_weights
+    torch.manual_seed(seed)
+    hp = Hparams.from_yamlfile(os.path.join(ROOT, "vae_gslm_b200", "configs", "train", "speech", "vae-gslm.yaml"))
+    model = LVTR(hp.model, input_dim=80)
+    model.apply(init_weights)
+    model = model.to(DEV)
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    lengths = torch.randint(T // 2, T + 1, (B,), generator=g)
+    lengths[0] = T
+    Tu = 150
+    ul = torch.randint(100, Tu + 1, (B,), generator=g)
+    tokens = torch.randint(0, 200, (B, T), generator=g)
+    mel = torch.randn(B, T, 80, generator=g)
+    batch = {"x": torch.cat([tokens[..., None].float(), mel], -1), "mask": torch.arange(T)[None] < lengths[:, None],
+             "utterance": torch.randn(B, Tu, 80, generator=g), "utt_mask": torch.arange(Tu)[None] < ul[:, None]}
+    g2 = torch.Generator(device="cpu").manual_seed(4321)
+    rng = {"eps_q": torch.randn(B, T, 4, generator=g2), "init_state": torch.rand(B, 1, 64, generator=g2) * 2 - 1,
+           "eps_p": torch.randn(B, T, 4, generator=g2), "diff_t": torch.randint(0, 1000, (B,), generator=g2),
+           "diff_noise": torch.randn(B, T, 80, generator=g2)}
+    batch = {k: v.to(DEV) for k, v in batch.items()}
+    rng = {k: v.to(DEV) for k, v in rng.items()}
+    cfg = Hparams.from_yamlfile(os.path.join(ROOT, "vae_gslm_b200", "configs", "train", "speech",
+                                             "vae-gslm.yaml")).model.to_dict()
+    return model, cfg, batch, rng
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_full_config_against_oracle(mode):
+    B, T = 2, 160
+    model, cfg, batch, rng = _full_model_and_batch(B, T)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and k in dict(model.named_parameters()))
+          for k, v in model.state_dict().items()}
+    ref = O.lvtr_forward(sd, cfg, batch["x"], batch["mask"], batch["utterance"], batch["utt_mask"], rng)
+    kw = 0.04
+    O.total_loss(ref, kw).backward()
+    model.set_compute_dtype(torch.float32 if mode == "fp32" else torch.bfloat16)
+    out = model(TensorMask(batch["x"], batch["mask"]), utterance=TensorMask(batch["utterance"], batch["utt_mask"]), **rng)
+    terms = assemble_loss(out, kld_weight=kw)
+    model.zero_grad()
+    terms["loss"].backward()
+    T_ = 1e-4 if mode == "fp32" else 2e-2
+    for mine, r in ((terms["loss"], O.total_loss(ref, kw)), (terms["kld"], ref["kld"]), (terms["token_kld"], ref["ce_loss"]),
+                    (terms["rec_loss"], ref["decoder_output"])):
+        assert abs(float(mine) - float(r)) / abs(float(r)) < T_
+    assert max_rel(out["logits"].value, ref["logits"]) < T_
+    assert max_rel(out["transformer_latent"].value, ref["transformer_latent"]) < (T_ if mode == "fp32" else 4e-2)
+    bad = []
+    for name, p in model.named_parameters():
+        e = frob_rel(p.grad, sd[name].grad)
+        if e > (3e-4 if mode == "fp32" else 6e-2):
+            bad.append((name, round(e, 5)))
+    assert not bad, bad[:20]

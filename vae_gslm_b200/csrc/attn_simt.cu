@@ -99,6 +99,7 @@ struct AttnShape {
   int B, H, Tq, Tk, q_offset;
   int64_t ld_q, ld_kv, ld_out;
   float scale;
+  int64_t kv_bs, kv_hs;     // K/V batch and head strides (elements): packed [B,T,H*D] or head-major cache
 };
 
 // ------------------------------------------------------------------------------------ forward
@@ -119,8 +120,8 @@ attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
   const float slope = slopes ? slopes[h] : 0.f;
 
   const T* qb = q + (int64_t)b * sh.Tq * sh.ld_q + h * AD;
-  const T* kb = k + (int64_t)b * sh.Tk * sh.ld_kv + h * AD;
-  const T* vb = v + (int64_t)b * sh.Tk * sh.ld_kv + h * AD;
+  const T* kb = k + (int64_t)b * sh.kv_bs + (int64_t)h * sh.kv_hs;
+  const T* vb = v + (int64_t)b * sh.kv_bs + (int64_t)h * sh.kv_hs;
   load_tile_t<T>(Qt, qb, sh.ld_q, q0, sh.Tq);
 
   float m[4], l[4], o[4][4];
@@ -249,8 +250,8 @@ attn_bwd_dkdv_kernel(const T* __restrict__ dout, const T* __restrict__ q, const 
   const int klen = kv_len ? min(kv_len[b], sh.Tk) : sh.Tk;
   const float slope = slopes ? slopes[h] : 0.f;
   const T* qb = q + (int64_t)b * sh.Tq * sh.ld_q + h * AD;
-  const T* kb = k + (int64_t)b * sh.Tk * sh.ld_kv + h * AD;
-  const T* vb = v + (int64_t)b * sh.Tk * sh.ld_kv + h * AD;
+  const T* kb = k + (int64_t)b * sh.kv_bs + (int64_t)h * sh.kv_hs;
+  const T* vb = v + (int64_t)b * sh.kv_bs + (int64_t)h * sh.kv_hs;
   const T* dob = dout + (int64_t)b * sh.Tq * bs.ld_dout + h * AD;
   const float* lse_row = lse + ((int64_t)b * sh.H + h) * sh.Tq;
   const float* delta_row = delta + ((int64_t)b * sh.H + h) * sh.Tq;
@@ -285,7 +286,7 @@ attn_bwd_dkdv_kernel(const T* __restrict__ dout, const T* __restrict__ q, const 
   for (int j = 0; j < 4; ++j) {
     const int jr = j0 + ty * 4 + j;
     if (jr >= sh.Tk) continue;
-    T* dkp = dk + ((int64_t)b * sh.Tk + jr) * bs.ld_dkv + h * AD + tx * 4;
+    T* dkp = dk + ((int64_t)b * sh.Tk + jr) * bs.ld_dkv + h * AD + tx * 4;   // gradients are always packed
     T* dvp = dv + ((int64_t)b * sh.Tk + jr) * bs.ld_dkv + h * AD + tx * 4;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -311,8 +312,8 @@ attn_bwd_dq_kernel(const T* __restrict__ dout, const T* __restrict__ q, const T*
   const int klen = kv_len ? min(kv_len[b], sh.Tk) : sh.Tk;
   const float slope = slopes ? slopes[h] : 0.f;
   const T* qb = q + (int64_t)b * sh.Tq * sh.ld_q + h * AD;
-  const T* kb = k + (int64_t)b * sh.Tk * sh.ld_kv + h * AD;
-  const T* vb = v + (int64_t)b * sh.Tk * sh.ld_kv + h * AD;
+  const T* kb = k + (int64_t)b * sh.kv_bs + (int64_t)h * sh.kv_hs;
+  const T* vb = v + (int64_t)b * sh.kv_bs + (int64_t)h * sh.kv_hs;
   const T* dob = dout + (int64_t)b * sh.Tq * bs.ld_dout + h * AD;
   const float* lse_row = lse + ((int64_t)b * sh.H + h) * sh.Tq;
   const float* delta_row = delta + ((int64_t)b * sh.H + h) * sh.Tq;
@@ -406,12 +407,13 @@ static int check_attn_shape(const char* fn, int64_t B, int64_t H, int64_t Tq, in
 
 extern "C" int vg_attn_fwd(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out,
                            int64_t ld_out, float* lse, const int32_t* kv_len, const float* slopes, int64_t B,
-                           int64_t H, int64_t Tq, int64_t Tk, int64_t D, int64_t q_offset, float scale, int dtype,
-                           vg_stream_t stream) {
+                           int64_t H, int64_t Tq, int64_t Tk, int64_t D, int64_t q_offset, int64_t kv_batch_stride,
+                           int64_t kv_head_stride, float scale, int dtype, vg_stream_t stream) {
   VG_REQUIRE(q && k && v && out && lse, -1, "vg_attn_fwd: null pointer");
   if (int rc = check_attn_shape("vg_attn_fwd", B, H, Tq, Tk, D, q_offset, dtype)) return rc;
-  VG_REQUIRE(ld_q >= H * D && ld_kv >= H * D && ld_out >= H * D, -3, "vg_attn_fwd: row stride too small");
-  AttnShape sh{(int)B, (int)H, (int)Tq, (int)Tk, (int)q_offset, ld_q, ld_kv, ld_out, scale};
+  VG_REQUIRE(ld_q >= H * D && ld_kv >= D && ld_out >= H * D, -3, "vg_attn_fwd: row stride too small");
+  AttnShape sh{(int)B, (int)H, (int)Tq, (int)Tk, (int)q_offset, ld_q, ld_kv, ld_out, scale,
+               kv_batch_stride > 0 ? kv_batch_stride : Tk * ld_kv, kv_head_stride > 0 ? kv_head_stride : D};
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VG_F32) return attn_fwd_launch<float>(q, k, v, out, lse, kv_len, slopes, sh, st);
   return attn_fwd_launch<__nv_bfloat16>(q, k, v, out, lse, kv_len, slopes, sh, st);
@@ -431,7 +433,8 @@ extern "C" int vg_attn_bwd(const void* dout, int64_t ld_dout, const void* q, con
   if (int rc = check_attn_shape("vg_attn_bwd", B, H, Tq, Tk, D, q_offset, dtype)) return rc;
   VG_REQUIRE(workspace && workspace_bytes >= vg_attn_bwd_workspace(B, H, Tq, Tk, D), -5,
              "vg_attn_bwd: workspace too small");
-  AttnBwdShape bs{{(int)B, (int)H, (int)Tq, (int)Tk, (int)q_offset, ld_q, ld_kv, ld_out, scale}, ld_dout, ld_dq, ld_dkv};
+  AttnBwdShape bs{{(int)B, (int)H, (int)Tq, (int)Tk, (int)q_offset, ld_q, ld_kv, ld_out, scale, Tk * ld_kv, D},
+                  ld_dout, ld_dq, ld_dkv};
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VG_F32)
     return attn_bwd_launch<float>(dout, q, k, v, out, lse, dq, dk, dv, kv_len, slopes, bs, (float*)workspace, st);

@@ -1,0 +1,661 @@
+"""Autograd-aware operators over the C-ABI kernels (``include/vgslm.h``).
+
+Each function here is the host-side mirror of one reference call site (cited per function); the
+math runs in libvgslm's CUDA kernels.  There is no CPU path: CPU tensors raise in ``_lib.ptr``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05
+
+# GEMM backend used for bf16 operands: AUTO picks tcgen05 when the shape qualifies.
+GEMM_BACKEND = GEMM_AUTO
+
+ACT_IDS = {"none": ACT_NONE, None: ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU,
+           "ReLU": ACT_RELU, "GELU": ACT_GELU}
+
+
+def _u8(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """bool [B,T] (or [M]) validity mask → flat uint8 view (no copy)."""
+    if mask is None:
+        return None
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    return mask.reshape(-1)
+
+
+def _rows2d(x: torch.Tensor) -> torch.Tensor:
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    return x2
+
+
+# ------------------------------------------------------------------------------------------- cast
+_shadow_cache = {}
+
+
+def lowp(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Compute-dtype copy of an fp32 master weight, refreshed when the master changes.
+
+    (The arena path in ``arena.py`` writes the bf16 shadow inside the fused AdamW kernel instead.)"""
+    if weight.dtype == dtype:
+        return weight.detach()
+    shadow = getattr(weight, "_vg_shadow", None)
+    if shadow is not None and shadow.dtype == dtype:
+        return shadow
+    key = (weight.data_ptr(), tuple(weight.shape), dtype)
+    ent = _shadow_cache.get(key)
+    ver = weight._version
+    if ent is not None and ent[0] == ver and ent[1].device == weight.device:
+        return ent[1]
+    src = weight.detach().contiguous()
+    out = torch.empty(src.shape, dtype=dtype, device=src.device)
+    L.call("vg_cast_f32_to_bf16", L.ptr(src), L.ptr(out), src.numel(), L.stream())
+    _shadow_cache[key] = (ver, out)
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    src = x.detach().contiguous()
+    out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    L.call("vg_cast_f32_to_bf16", L.ptr(src), L.ptr(out), src.numel(), L.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bool = True,
+         out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+         bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         preact: Optional[torch.Tensor] = None, dact_src: Optional[torch.Tensor] = None, dact: int = ACT_NONE,
+         residual: Optional[torch.Tensor] = None, row_mask: Optional[torch.Tensor] = None,
+         mask_first: bool = False, beta: float = 0.0, backend: Optional[int] = None) -> torch.Tensor:
+    """C = epilogue(op(A)·op(B)); see vg_gemm in include/vgslm.h.  ``a``/``b`` are 2-D with unit inner stride."""
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    assert a.dtype == b.dtype, (a.dtype, b.dtype)
+    if trans_a:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if trans_b:
+        N, Kb = b.shape
+    else:
+        Kb, N = b.shape
+    assert K == Kb, f"inner dimensions differ: {K} vs {Kb}"
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype or a.dtype, device=a.device)
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    g = L.GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    g.A, g.lda, g.trans_a = L.ptr(a), a.stride(0), int(trans_a)
+    g.B, g.ldb, g.trans_b = L.ptr(b), b.stride(0), int(trans_b)
+    g.C, g.ldc = L.ptr(out), out.stride(0)
+    g.ab_dtype, g.c_dtype = L.dtype_id(a.dtype), L.dtype_id(out.dtype)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+        g.bias = L.ptr(bias)
+    g.act, g.dact = act, dact
+    for name, t, ld in (("preact", preact, "ld_preact"), ("dact_src", dact_src, "ld_dact"),
+                        ("residual", residual, "ld_res")):
+        if t is not None:
+            assert t.dtype == out.dtype and t.shape == (M, N) and t.stride(1) == 1, name
+            setattr(g, name, L.ptr(t))
+            setattr(g, ld, t.stride(0))
+    if row_mask is not None:
+        assert row_mask.numel() == M
+        g.row_mask = L.ptr(row_mask)
+    g.mask_before_residual = int(mask_first)
+    g.beta = beta
+    be = GEMM_BACKEND if backend is None else backend
+    L.call("vg_gemm", C.byref(g), be, None, 0, L.stream())
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    ws = L.workspace(L.load().vg_colsum_workspace(rows, cols), x.device)
+    L.call("vg_colsum", L.ptr(x), x.stride(0), L.ptr(out), rows, cols, L.dtype_id(x.dtype), L.ptr(ws), ws.numel(),
+           L.stream())
+    return out
+
+
+def mask_rows_(x2: torch.Tensor, mask_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = where(mask[row], x, 0) on a contiguous 2-D tensor (utils/tensormask.py:63-67)."""
+    assert x2.is_contiguous()
+    out = torch.empty_like(x2) if out is None else out
+    L.call("vg_mask_rows", L.ptr(x2), L.ptr(mask_u8), L.ptr(out), x2.shape[0], x2.shape[1], L.dtype_id(x2.dtype),
+           L.stream())
+    return out
+
+
+def act_bwd(dy: torch.Tensor, src: torch.Tensor, act: int) -> torch.Tensor:
+    assert dy.is_contiguous() and src.is_contiguous() and dy.dtype == src.dtype
+    out = torch.empty_like(dy)
+    L.call("vg_act_bwd", L.ptr(dy), L.ptr(src), L.ptr(out), dy.numel(), act, L.dtype_id(dy.dtype), L.stream())
+    return out
+
+
+class _MaskRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask_u8):
+        ctx.save_for_backward(mask_u8)
+        ctx.shape = x.shape
+        return mask_rows_(_rows2d(x).contiguous(), mask_u8).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask_u8,) = ctx.saved_tensors
+        return mask_rows_(_rows2d(dy).contiguous(), mask_u8).view(ctx.shape), None
+
+
+def mask_rows(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """TensorMask.apply_mask for [B,T,C] activations with C % 8 == 0."""
+    return _MaskRows.apply(x, _u8(mask))
+
+
+# ---------------------------------------------------------------------------------------- RMSNorm
+class _RMSNorm(torch.autograd.Function):
+    """modules/norm.py:22-32 (+ the mask of transformer/layers.py:53-54)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, eps, mask_u8, out_dtype):
+        x2 = _rows2d(x).contiguous()
+        rows, dim = x2.shape
+        y = torch.empty((rows, dim), dtype=out_dtype or x.dtype, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        sc = scale.detach().float().contiguous()
+        L.call("vg_rmsnorm_fwd", L.ptr(x2), L.ptr(sc), L.ptr(mask_u8), L.ptr(y), L.ptr(rstd), rows, dim, float(eps),
+               L.dtype_id(x2.dtype), L.dtype_id(y.dtype), L.stream())
+        ctx.save_for_backward(x2, sc, rstd, mask_u8)
+        ctx.xshape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, sc, rstd, mask_u8 = ctx.saved_tensors
+        rows, dim = x2.shape
+        dy2 = _rows2d(dy).contiguous()
+        dx = torch.empty_like(x2)
+        dscale = torch.empty(dim, dtype=torch.float32, device=x2.device)
+        ws = L.workspace(L.load().vg_rmsnorm_bwd_workspace(rows, dim), x2.device)
+        L.call("vg_rmsnorm_bwd", L.ptr(dy2), L.ptr(x2), L.ptr(sc), L.ptr(rstd), L.ptr(mask_u8), None, L.ptr(dx),
+               L.ptr(dscale), L.ptr(ws), ws.numel(), rows, dim, L.dtype_id(x2.dtype), L.dtype_id(dy2.dtype),
+               L.stream())
+        return dx.view(ctx.xshape), dscale, None, None, None
+
+
+def rmsnorm(x: torch.Tensor, scale: torch.Tensor, eps: float, mask: Optional[torch.Tensor] = None,
+            out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    return _RMSNorm.apply(x, scale, eps, _u8(mask), out_dtype)
+
+
+# ----------------------------------------------------------------------------------------- Linear
+class _Linear(torch.autograd.Function):
+    """y = mask/residual epilogue(act(x·Wᵀ + b)) — one GEMM launch; backward = dgrad + wgrad (+ colsum)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, mask_u8, act, mask_first, out_dtype, w_compute):
+        x2 = _rows2d(x)
+        w = w_compute if w_compute is not None else lowp(weight, x2.dtype)
+        N = w.shape[0]
+        odt = out_dtype or x2.dtype
+        res2 = _rows2d(residual) if residual is not None else None
+        b = bias.detach().float() if bias is not None else None
+        need_pre = act != ACT_NONE and (act == ACT_GELU or residual is not None or mask_u8 is not None)
+        pre = torch.empty((x2.shape[0], N), dtype=odt, device=x.device) if need_pre else None
+        y = gemm(x2, w, trans_b=True, out_dtype=odt, bias=b, act=act, preact=pre, residual=res2,
+                 row_mask=mask_u8, mask_first=mask_first)
+        ctx.save_for_backward(x2, w, pre if need_pre else (y if act != ACT_NONE else None), mask_u8)
+        ctx.meta = (act, mask_first, x.shape, weight.dtype, bias is not None, residual is not None,
+                    residual.shape if residual is not None else None)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, act_src, mask_u8 = ctx.saved_tensors
+        act, mask_first, xshape, wdtype, has_bias, has_res, res_shape = ctx.meta
+        dy2 = _rows2d(dy).contiguous()
+        g = mask_rows_(dy2, mask_u8) if mask_u8 is not None else dy2
+        dres = None
+        if has_res and ctx.needs_input_grad[3]:
+            dres = (dy2 if mask_first else g).view(res_shape)
+        dpre = act_bwd(g, act_src, act) if act != ACT_NONE else g
+        if dpre.dtype != x2.dtype:           # fp32 head outputs of bf16 GEMMs
+            dpre = dpre.to(x2.dtype)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dpre, w, trans_b=False).view(xshape)
+        if ctx.needs_input_grad[1]:
+            dw = gemm(dpre, x2, trans_a=True, trans_b=False, out_dtype=torch.float32)
+            if wdtype != torch.float32:
+                dw = dw.to(wdtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dpre)
+        return dx, dw, db, dres, None, None, None, None, None
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+           act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, row_mask: Optional[torch.Tensor] = None,
+           mask_before_residual: bool = False, out_dtype: Optional[torch.dtype] = None,
+           w_compute: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.Linear (+ fused activation / residual / TensorMask.apply_mask) on the last dimension of ``x``."""
+    return _Linear.apply(x, weight, bias, residual, _u8(row_mask), act, mask_before_residual, out_dtype, w_compute)
+
+
+class _FFN(torch.autograd.Function):
+    """transformer/layers.py:82-86: out = mask(res + W2·act(W1·x + b1) + b2).
+
+    Forward: GEMM1 stores the pre-activation and the activation from one epilogue; GEMM2 fuses bias,
+    residual and row mask.  Backward: the GELU derivative rides in the epilogue of GEMM2's dgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual, mask_u8, act):
+        x2 = _rows2d(x)
+        w1c, w2c = lowp(w1, x2.dtype), lowp(w2, x2.dtype)
+        M, F = x2.shape[0], w1c.shape[0]
+        pre = torch.empty((M, F), dtype=x2.dtype, device=x.device)
+        h = gemm(x2, w1c, trans_b=True, bias=b1.detach().float() if b1 is not None else None, act=act, preact=pre)
+        res2 = _rows2d(residual) if residual is not None else None
+        y = gemm(h, w2c, trans_b=True, bias=b2.detach().float() if b2 is not None else None, residual=res2,
+                 row_mask=mask_u8)
+        ctx.save_for_backward(x2, w1c, w2c, pre, h, mask_u8)
+        ctx.meta = (act, x.shape, b1 is not None, b2 is not None, residual is not None)
+        return y.view(x.shape[:-1] + (w2c.shape[0],))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1c, w2c, pre, h, mask_u8 = ctx.saved_tensors
+        act, xshape, has_b1, has_b2, has_res = ctx.meta
+        dy2 = _rows2d(dy).contiguous()
+        g = mask_rows_(dy2, mask_u8) if mask_u8 is not None else dy2
+        dres = g.view(dy.shape) if has_res and ctx.needs_input_grad[5] else None
+        dpre = gemm(g, w2c, trans_b=False, dact_src=pre, dact=act)            # (g·W2) ⊙ act'(pre)
+        dw2 = gemm(g, h, trans_a=True, trans_b=False, out_dtype=torch.float32) if ctx.needs_input_grad[3] else None
+        db2 = colsum(g) if has_b2 and ctx.needs_input_grad[4] else None
+        dx = gemm(dpre, w1c, trans_b=False).view(xshape) if ctx.needs_input_grad[0] else None
+        dw1 = gemm(dpre, x2, trans_a=True, trans_b=False, out_dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        db1 = colsum(dpre) if has_b1 and ctx.needs_input_grad[2] else None
+        return dx, dw1, db1, dw2, db2, dres, None, None
+
+
+def ffn(x, w1, b1, w2, b2, residual=None, row_mask=None, act: int = ACT_GELU) -> torch.Tensor:
+    return _FFN.apply(x, w1, b1, w2, b2, residual, _u8(row_mask), act)
+
+
+# -------------------------------------------------------------------------------------- attention
+def alibi_slopes(nheads: int) -> list:
+    """Head slopes of position/alibi.py:19-30 (geometric sequence; interleaved for non powers of two)."""
+    def pow2(n):
+        start = 2.0 ** (-(2.0 ** -(math.log2(n) - 3)))
+        return [start * (start ** i) for i in range(n)]
+    if math.log2(nheads).is_integer():
+        return pow2(nheads)
+    c = 2 ** math.floor(math.log2(nheads))
+    return pow2(c) + alibi_slopes(2 * c)[0::2][: nheads - c]
+
+
+class _Attention(torch.autograd.Function):
+    """attention.py:52-78 — causal softmax(QKᵀ/√D + ALiBi) V with key-padding, packed qkv in/out."""
+
+    @staticmethod
+    def forward(ctx, qkv, kv_len, slopes, nheads, scale):
+        B, T, C3 = qkv.shape
+        HD = C3 // 3
+        D = HD // nheads
+        qkv = qkv.contiguous()
+        q, k, v = qkv[..., :HD], qkv[..., HD:2 * HD], qkv[..., 2 * HD:]
+        out = torch.empty((B, T, HD), dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty((B, nheads, T), dtype=torch.float32, device=qkv.device)
+        L.call("vg_attn_fwd", L.ptr(q), L.ptr(k), L.ptr(v), C3, C3, L.ptr(out), HD, L.ptr(lse), L.ptr(kv_len),
+               L.ptr(slopes), B, nheads, T, T, D, 0, 0, 0, float(scale), L.dtype_id(qkv.dtype), L.stream())
+        ctx.save_for_backward(qkv, out, lse, kv_len, slopes)
+        ctx.meta = (nheads, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse, kv_len, slopes = ctx.saved_tensors
+        nheads, scale = ctx.meta
+        B, T, C3 = qkv.shape
+        HD = C3 // 3
+        D = HD // nheads
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        q, k, v = qkv[..., :HD], qkv[..., HD:2 * HD], qkv[..., 2 * HD:]
+        dq, dk, dv = dqkv[..., :HD], dqkv[..., HD:2 * HD], dqkv[..., 2 * HD:]
+        ws = L.workspace(L.load().vg_attn_bwd_workspace(B, nheads, T, T, D), qkv.device)
+        L.call("vg_attn_bwd", L.ptr(dout), HD, L.ptr(q), L.ptr(k), L.ptr(v), C3, C3, L.ptr(out), HD, L.ptr(lse),
+               L.ptr(dq), L.ptr(dk), L.ptr(dv), C3, C3, L.ptr(kv_len), L.ptr(slopes), B, nheads, T, T, D, 0,
+               float(scale), L.dtype_id(qkv.dtype), L.ptr(ws), ws.numel(), L.stream())
+        return dqkv, None, None, None, None
+
+
+def attention(qkv: torch.Tensor, nheads: int, kv_len: Optional[torch.Tensor] = None,
+              slopes: Optional[torch.Tensor] = None, scale: Optional[float] = None) -> torch.Tensor:
+    """Self-attention over a packed [B,T,3·H·D] projection; kv_len int32 [B] = valid (right-padded) lengths."""
+    HD = qkv.shape[-1] // 3
+    scale = scale if scale is not None else 1.0 / math.sqrt(HD // nheads)
+    return _Attention.apply(qkv, kv_len, slopes, nheads, scale)
+
+
+def attention_cached(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, nheads: int, q_offset: int,
+                     slopes: Optional[torch.Tensor], scale: Optional[float] = None,
+                     head_major: bool = False, tk: Optional[int] = None) -> torch.Tensor:
+    """Inference attention of Tq new queries against Tk keys (q_offset = Tk − Tq), no grad.
+
+    ``k``/``v`` are [B,Tk,H·D] views (packed or separate) or, with ``head_major``, a [B,H,Tmax,D] cache
+    of which the first ``tk`` rows are attended."""
+    B, Tq, HD = q.shape
+    D = HD // nheads
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    assert q.stride(2) == 1 and q.stride(0) == Tq * q.stride(1)
+    if head_major:
+        assert k.is_contiguous() and v.is_contiguous() and k.shape == v.shape and k.shape[1] == nheads
+        Tk, ld_kv, bs, hs = int(tk), D, k.stride(0), k.stride(1)
+    else:
+        Tk, ld_kv = k.shape[1], k.stride(1)
+        assert k.stride(2) == 1 and v.stride(2) == 1 and v.stride(1) == ld_kv and k.stride(0) == v.stride(0)
+        bs, hs = k.stride(0), D
+    out = torch.empty((B, Tq, HD), dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, nheads, Tq), dtype=torch.float32, device=q.device)
+    L.call("vg_attn_fwd", L.ptr(q), L.ptr(k), L.ptr(v), q.stride(1), ld_kv, L.ptr(out), HD, L.ptr(lse), None,
+           L.ptr(slopes), B, nheads, Tq, Tk, D, q_offset, bs, hs, float(scale), L.dtype_id(q.dtype), L.stream())
+    return out
+
+
+@torch.no_grad()
+def kv_append(k: torch.Tensor, v: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, pos: int) -> None:
+    """copy new K/V rows [B,T,H·D] (views of a packed projection) into the head-major cache at ``pos``."""
+    B, T, HD = k.shape
+    _, H, Tmax, D = k_cache.shape
+    assert k.stride(2) == 1 and v.stride(1) == k.stride(1) and k.stride(0) == T * k.stride(1)
+    L.call("vg_kv_append", L.ptr(k), L.ptr(v), k.stride(1), L.ptr(k_cache), L.ptr(v_cache), B, H, D, T, Tmax, pos,
+           L.dtype_id(k.dtype), L.stream())
+
+
+@torch.no_grad()
+def attention_decode(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, pos: int,
+                     slopes: Optional[torch.Tensor], pos_dev: Optional[torch.Tensor] = None,
+                     scale: Optional[float] = None, splits: Optional[int] = None) -> torch.Tensor:
+    """single-token step: append this token's k/v at ``pos`` and attend over cache rows [0, pos]."""
+    B, C3 = qkv.shape
+    _, H, Tmax, D = k_cache.shape
+    scale = scale if scale is not None else 1.0 / math.sqrt(D)
+    if splits is None:      # fill ~2 waves of 148 SMs when the batch alone cannot
+        splits = max(1, min(16, (2 * 148 + B * H - 1) // (B * H), (pos + 64) // 64))
+    out = torch.empty((B, C3 // 3), dtype=qkv.dtype, device=qkv.device)
+    ws = L.workspace(L.load().vg_attn_decode_workspace(B, H, D, splits), qkv.device)
+    L.call("vg_attn_decode", L.ptr(qkv), L.ptr(k_cache), L.ptr(v_cache), L.ptr(out), L.ptr(slopes), B, H, D, Tmax,
+           pos, L.ptr(pos_dev), splits, float(scale), L.dtype_id(qkv.dtype), L.ptr(ws), ws.numel(), L.stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------- latent
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if t is None else t.detach().float().contiguous()
+
+
+class _LatentFront(torch.autograd.Function):
+    """lvtr.py:151-169 fused: posterior heads + reparameterisation + log_q + embedding + fuse + BOS shift."""
+
+    @staticmethod
+    def forward(ctx, h_enc, eps, ids, mask_u8, init_state, w_mean, b_mean, w_logstd, b_logstd, tok_emb, w_fuse,
+                b_fuse, temperature, act_dtype):
+        ctx.set_materialize_grads(False)
+        B, T, Ld = h_enc.shape
+        E = tok_emb.shape[1]
+        dev = h_enc.device
+        a = L.LatentFrontArgs()
+        a.B, a.T, a.latent_dim, a.emb_dim, a.vocab = B, T, Ld, E, tok_emb.shape[0]
+        keep = dict(h_enc=_f32c(h_enc), eps=_f32c(eps), ids=ids.contiguous(), mask=mask_u8,
+                    init_state=_f32c(init_state), w_mean=_f32c(w_mean), b_mean=_f32c(b_mean),
+                    w_logstd=_f32c(w_logstd), b_logstd=_f32c(b_logstd), tok_emb=_f32c(tok_emb),
+                    w_fuse=_f32c(w_fuse), b_fuse=_f32c(b_fuse))
+        assert keep["ids"].dtype == torch.int64
+        for kname, t in keep.items():
+            setattr(a, kname, L.ptr(t))
+        a.temperature = float(temperature)
+        f32 = dict(dtype=torch.float32, device=dev)
+        mean, logstd, z, log_q = (torch.empty((B, T, Ld), **f32) for _ in range(4))
+        u = torch.empty((B, T, E), dtype=act_dtype, device=dev)
+        u_shift = torch.empty((B, T, E), dtype=act_dtype, device=dev)
+        a.mean, a.logstd, a.z, a.log_q = L.ptr(mean), L.ptr(logstd), L.ptr(z), L.ptr(log_q)
+        a.u, a.u_shift, a.act_dtype = L.ptr(u), L.ptr(u_shift), L.dtype_id(act_dtype)
+        L.call("vg_latent_front_fwd", C.byref(a), L.stream())
+        ctx.keep = keep
+        ctx.outs = (mean, logstd, z, log_q)
+        ctx.meta = (B, T, Ld, E, float(temperature), act_dtype)
+        return mean, logstd, z, log_q, u, u_shift
+
+    @staticmethod
+    def backward(ctx, d_mean, d_logstd, d_z, d_log_q, d_u, d_u_shift):
+        B, T, Ld, E, temperature, act_dtype = ctx.meta
+        keep = ctx.keep
+        mean, logstd, z, log_q = ctx.outs
+        dev = mean.device
+        g = L.LatentFrontBwdArgs()
+        a = g.f
+        a.B, a.T, a.latent_dim, a.emb_dim, a.vocab = B, T, Ld, E, keep["tok_emb"].shape[0]
+        for kname, t in keep.items():
+            setattr(a, kname, L.ptr(t))
+        a.temperature = temperature
+        a.mean, a.logstd, a.z, a.log_q = L.ptr(mean), L.ptr(logstd), L.ptr(z), L.ptr(log_q)
+        a.u, a.u_shift, a.act_dtype = L.ptr(mean), L.ptr(mean), L.dtype_id(act_dtype)   # not read by backward
+        holders = []
+
+        def f32(t):
+            if t is None:
+                return None
+            t = t.float().contiguous()
+            holders.append(t)
+            return L.ptr(t)
+
+        def act(t):
+            if t is None:
+                return None
+            t = t.to(act_dtype).contiguous()
+            holders.append(t)
+            return L.ptr(t)
+
+        g.d_z, g.d_log_q, g.d_mean_out, g.d_logstd_out = f32(d_z), f32(d_log_q), f32(d_mean), f32(d_logstd)
+        g.d_u, g.d_u_shift = act(d_u), act(d_u_shift)
+        o = dict(dtype=torch.float32, device=dev)
+        d_h = torch.empty((B, T, Ld), **o)
+        dwm, dws = torch.empty((Ld, Ld), **o), torch.empty((Ld, Ld), **o)
+        dbm, dbs = torch.empty(Ld, **o), torch.empty(Ld, **o)
+        demb = torch.empty_like(keep["tok_emb"])
+        dwf, dbf = torch.empty((E, Ld), **o), torch.empty(E, **o)
+        g.d_h_enc = L.ptr(d_h)
+        g.d_w_mean, g.d_b_mean, g.d_w_logstd, g.d_b_logstd = L.ptr(dwm), L.ptr(dbm), L.ptr(dws), L.ptr(dbs)
+        g.d_tok_emb, g.d_w_fuse, g.d_b_fuse = L.ptr(demb), L.ptr(dwf), L.ptr(dbf)
+        ws = L.workspace(L.load().vg_latent_front_bwd_workspace(B, T, Ld, E, keep["tok_emb"].shape[0]), dev)
+        L.call("vg_latent_front_bwd", C.byref(g), L.ptr(ws), ws.numel(), L.stream())
+        return d_h, None, None, None, None, dwm, dbm, dws, dbs, demb, dwf, dbf, None, None
+
+
+def latent_front(h_enc, eps, ids, mask, init_state, w_mean, b_mean, w_logstd, b_logstd, tok_emb, w_fuse, b_fuse,
+                 temperature: float = 1.0, act_dtype: torch.dtype = torch.float32):
+    """→ (mean, logstd, z, log_q) f32 [B,T,L] and (u, u_shift) act-dtype [B,T,E]."""
+    return _LatentFront.apply(h_enc, eps, ids, _u8(mask), init_state, w_mean, b_mean, w_logstd, b_logstd, tok_emb,
+                              w_fuse, b_fuse, temperature, act_dtype)
+
+
+def _fill_back_args(a, head, z, log_q, mask_u8, flow, ln_eps, lo, hi):
+    w1, b1, lnw, lnb, w2, b2 = flow
+    M = head.shape[0]
+    a.M, a.latent_dim, a.hidden, a.n_layers = M, w2.shape[1], w1.shape[1], w1.shape[0]
+    a.head, a.head_ld = L.ptr(head), head.stride(0)
+    a.z, a.log_q, a.mask = L.ptr(z), L.ptr(log_q), L.ptr(mask_u8)
+    a.w1, a.b1, a.ln_w, a.ln_b, a.w2, a.b2 = (L.ptr(t) for t in (w1, b1, lnw, lnb, w2, b2))
+    a.ln_eps, a.scale_lo, a.scale_hi = float(ln_eps), float(lo), float(hi)
+
+
+class _LatentBack(torch.autograd.Function):
+    """lvtr.py:172-191 fused: prior head columns + 4 conditional coupling layers + log_p + KL."""
+
+    @staticmethod
+    def forward(ctx, head, z, log_q, mask_u8, w1, b1, lnw, lnb, w2, b2, ln_eps, lo, hi):
+        ctx.set_materialize_grads(False)
+        head2 = head.reshape(-1, head.shape[-1])
+        assert head2.dtype == torch.float32 and head2.stride(1) == 1
+        M = head2.shape[0]
+        Ld = w2.shape[1]
+        z2, lq2 = _f32c(z).reshape(M, Ld), _f32c(log_q).reshape(M, Ld)
+        flow = tuple(_f32c(t) for t in (w1, b1, lnw, lnb, w2, b2))
+        dev = head.device
+        log_p = torch.empty((M, Ld), dtype=torch.float32, device=dev)
+        y = torch.empty((M, Ld), dtype=torch.float32, device=dev)
+        kl_frame = torch.empty(M, dtype=torch.float32, device=dev)
+        kl_sum = torch.empty(1, dtype=torch.float32, device=dev)
+        a = L.LatentBackArgs()
+        _fill_back_args(a, head2, z2, lq2, mask_u8, flow, ln_eps, lo, hi)
+        a.log_p, a.y, a.kl_frame, a.kl_sum = L.ptr(log_p), L.ptr(y), L.ptr(kl_frame), L.ptr(kl_sum)
+        ws = L.workspace(L.load().vg_latent_back_workspace(M, Ld, w1.shape[1], w1.shape[0]), dev)
+        L.call("vg_latent_back_fwd", C.byref(a), L.ptr(ws), ws.numel(), L.stream())
+        ctx.keep = (head2, z2, lq2, mask_u8, flow, float(ln_eps), float(lo), float(hi))
+        ctx.shapes = (head.shape, z.shape)
+        lead = z.shape[:-1]
+        return log_p.view(*lead, Ld), y.view(*lead, Ld), kl_sum.view(())
+
+    @staticmethod
+    def backward(ctx, d_log_p, d_y, d_kl):
+        if d_y is not None:
+            raise NotImplementedError("gradient through the flow output `y` alone is not part of the hot path")
+        head2, z2, lq2, mask_u8, flow, ln_eps, lo, hi = ctx.keep
+        head_shape, z_shape = ctx.shapes
+        M, Ld = z2.shape
+        dev = head2.device
+        maskf = mask_u8.view(M, 1).float()
+        dlp = torch.zeros((M, Ld), dtype=torch.float32, device=dev) if d_log_p is None \
+            else d_log_p.reshape(M, Ld).float()
+        d_log_q = None
+        if d_kl is not None:      # kl = Σ_valid mean_c(log_q − log_p)
+            dlp = dlp - (d_kl.float() / Ld) * maskf
+            d_log_q = ((d_kl.float() / Ld) * maskf).expand(M, Ld).reshape(z_shape).contiguous()
+        dlp = dlp.contiguous()
+        g = L.LatentBackBwdArgs()
+        _fill_back_args(g.f, head2, z2, lq2, mask_u8, flow, ln_eps, lo, hi)
+        d_head = torch.empty_like(head2)
+        if head2.shape[1] > 2 * Ld + flow[0].shape[0] * 2 * flow[0].shape[1]:
+            d_head.zero_()           # padded columns beyond the used head layout
+        d_z = torch.empty((M, Ld), dtype=torch.float32, device=dev)
+        grads = tuple(torch.empty_like(t) for t in flow)
+        g.d_log_p, g.d_head, g.d_z = L.ptr(dlp), L.ptr(d_head), L.ptr(d_z)
+        g.d_w1, g.d_b1, g.d_ln_w, g.d_ln_b, g.d_w2, g.d_b2 = (L.ptr(t) for t in grads)
+        ws = L.workspace(L.load().vg_latent_back_workspace(M, Ld, flow[0].shape[1], flow[0].shape[0]), dev)
+        L.call("vg_latent_back_bwd", C.byref(g), L.ptr(ws), ws.numel(), L.stream())
+        return (d_head.view(head_shape), d_z.view(z_shape), d_log_q, None, *grads, None, None, None)
+
+
+def latent_back(head, z, log_q, mask, w1, b1, lnw, lnb, w2, b2, ln_eps: float, scale_lo: float, scale_hi: float):
+    """→ (log_p [..,L] masked, y [..,L] flow output, kl_sum scalar)."""
+    return _LatentBack.apply(head, z, log_q, _u8(mask), w1, b1, lnw, lnb, w2, b2, ln_eps, scale_lo, scale_hi)
+
+
+@torch.no_grad()
+def latent_prior_sample(head, eps, temperature, w1, b1, lnw, lnb, w2, b2, ln_eps, scale_lo, scale_hi):
+    """lvtr.py:267-275: z = Flow⁻¹(mean_p + exp(logstd_p)·eps·τ; FiLM columns of ``head``)."""
+    head2 = head.reshape(-1, head.shape[-1])
+    M, Ld = head2.shape[0], w2.shape[1]
+    flow = tuple(_f32c(t) for t in (w1, b1, lnw, lnb, w2, b2))
+    a = L.LatentBackArgs()
+    dummy = head2
+    _fill_back_args(a, head2, dummy, dummy, None, flow, ln_eps, scale_lo, scale_hi)
+    e = _f32c(eps).reshape(M, Ld) if eps is not None else None
+    z = torch.empty((M, Ld), dtype=torch.float32, device=head.device)
+    L.call("vg_latent_prior_sample", C.byref(a), L.ptr(e), float(temperature), L.ptr(z), L.stream())
+    return z.view(*head.shape[:-1], Ld)
+
+
+# ----------------------------------------------------------------------------------------- losses
+class _SoftmaxCE(torch.autograd.Function):
+    """losses.py:30-41 — Σ over valid rows of −log softmax(logits)[target]."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, mask_u8):
+        lg = _rows2d(logits)
+        rows, vocab = lg.shape
+        tg = targets.reshape(-1).contiguous()
+        dev = lg.device
+        lse = torch.empty(rows, dtype=torch.float32, device=dev)
+        loss_rows = torch.empty(rows, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = L.workspace(L.load().vg_softmax_ce_workspace(rows), dev)
+        L.call("vg_softmax_ce_fwd", L.ptr(lg), lg.stride(0), L.ptr(tg), L.ptr(mask_u8), L.ptr(lse), L.ptr(loss_rows),
+               L.ptr(loss), rows, vocab, L.dtype_id(lg.dtype), L.ptr(ws), ws.numel(), L.stream())
+        ctx.save_for_backward(lg, tg, mask_u8, lse)
+        ctx.shape = logits.shape
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        lg, tg, mask_u8, lse = ctx.saved_tensors
+        rows, vocab = lg.shape
+        dl = d_loss.float().reshape(1).contiguous()
+        d_logits = torch.empty((rows, vocab), dtype=lg.dtype, device=lg.device)
+        L.call("vg_softmax_ce_bwd", L.ptr(lg), lg.stride(0), L.ptr(tg), L.ptr(mask_u8), L.ptr(lse), L.ptr(dl),
+               L.ptr(d_logits), vocab, rows, vocab, L.dtype_id(lg.dtype), L.stream())
+        return d_logits.view(ctx.shape), None, None
+
+
+def softmax_ce(logits: torch.Tensor, targets: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _SoftmaxCE.apply(logits, targets, _u8(mask))
+
+
+@torch.no_grad()
+def qsample(x0, noise, t, sqrt_ac, sqrt_1mac, mask, x0_scale: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """ddpm.py:328-334,352-359: x_t = (√ᾱ_t·x0·scale + √(1−ᾱ_t)·noise)·mask ; target = noise·mask."""
+    B, T, Cc = x0.shape
+    x0c, nc = _f32c(x0), _f32c(noise)
+    x_t, target = torch.empty_like(x0c), torch.empty_like(x0c)
+    L.call("vg_qsample", L.ptr(x0c), L.ptr(nc), L.ptr(t.contiguous()), L.ptr(_f32c(sqrt_ac)), L.ptr(_f32c(sqrt_1mac)),
+           L.ptr(_u8(mask)), float(x0_scale), L.ptr(x_t), L.ptr(target), B, T, Cc, L.stream())
+    return x_t, target
+
+
+class _MaskedL1(torch.autograd.Function):
+    """losses.py:9-27,44-57 — Σ_{b,t valid} mean_c |pred − target|."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mask_u8):
+        B, T, Cc = pred.shape
+        p, tg = pred.contiguous(), target.contiguous()
+        assert p.dtype == torch.float32 and tg.dtype == torch.float32
+        loss = torch.empty(1, dtype=torch.float32, device=p.device)
+        ws = L.workspace(L.load().vg_masked_l1_workspace(B, T, Cc), p.device)
+        L.call("vg_masked_l1_fwd", L.ptr(p), L.ptr(tg), L.ptr(mask_u8), L.ptr(loss), B, T, Cc, L.ptr(ws), ws.numel(),
+               L.stream())
+        ctx.save_for_backward(p, tg, mask_u8)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        p, tg, mask_u8 = ctx.saved_tensors
+        B, T, Cc = p.shape
+        dl = d_loss.float().reshape(1).contiguous()
+        d_pred = torch.empty_like(p)
+        L.call("vg_masked_l1_bwd", L.ptr(p), L.ptr(tg), L.ptr(mask_u8), L.ptr(dl), L.ptr(d_pred), B, T, Cc, L.stream())
+        return d_pred, None, None
+
+
+def masked_l1(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    return _MaskedL1.apply(pred.float(), target.float(), _u8(mask))
+
+
+@torch.no_grad()
+def sample_token(logits: torch.Tensor, u: Optional[torch.Tensor], temperature: float = 1.0) -> torch.Tensor:
+    """lvtr.py:277-285.  ``u`` = U[0,1) per row → inverse-CDF multinomial; ``u=None`` → greedy argmax."""
+    lg = _rows2d(logits)
+    rows, vocab = lg.shape
+    out = torch.empty(rows, dtype=torch.int64, device=lg.device)
+    uu = _f32c(u).reshape(-1) if u is not None else None
+    L.call("vg_sample_token", L.ptr(lg), lg.stride(0), L.ptr(uu), float(temperature), L.ptr(out), rows, vocab,
+           L.dtype_id(lg.dtype), L.stream())
+    return out.view(logits.shape[:-1])
