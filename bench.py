@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — VAE-GSLM hot-path benchmark (contract: see the task brief / DESIGN.md §Measurement).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (N>1: launched by torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   the reference algorithm (oracle port) on host cores
+
+A "step" is one full training step of BASELINE.json configs[1] on one synthetic micro-batch per GPU:
+forward + backward of LVTR (bf16 activations, tcgen05 GEMMs), data-parallel gradient all-reduce (N>1) and the
+fused AdamW update.  `value` = frames of ALL ranks / max-over-ranks device time, inputs resident in HBM;
+`e2e` repeats the measurement with pinned HOST inputs copied in and the loss read back every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = os.path.join(ROOT, "vae_gslm_b200", "configs", "train", "speech", "vae-gslm.yaml")
+N_MELS, VOCAB, KW = 80, 200, 0.04
+
+
+def train_flops_per_frame(T: int) -> float:
+    """fwd MAC/frame = LM-side 204,228,384 + attention 16,384·(T+1) + conv encoder 6,345,216 +
+    UNet 14,527,488; train FLOPs = 6 × MAC."""
+    return 6.0 * (204_228_384 + 16_384 * (T + 1) + 6_345_216 + 14_527_488)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"bf16_burst": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "hbm_gbs": d["hbm_gbs"], "src": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+def synthetic_batch(B, T, rank, pin=False):
+    """SURVEY §8d synthetic inputs: tokens ~ randint(0,200), mel ~ N(0,1), utterance crop N(0,1)[B,150,80] with
+    lengths ~ U{100..150}; full-length regime (all lengths = T)."""
+    g = torch.Generator().manual_seed(1234 + rank)
+    tokens = torch.randint(0, VOCAB, (B, T), generator=g)
+    mel = torch.randn(B, T, N_MELS, generator=g)
+    x = torch.cat([tokens[..., None].float(), mel], -1)
+    ul = torch.randint(100, 151, (B,), generator=g)
+    utt = torch.randn(B, 150, N_MELS, generator=g)
+    batch = {"x": x, "mask": torch.ones(B, T, dtype=torch.bool), "utterance": utt,
+             "utt_mask": torch.arange(150)[None, :] < ul[:, None]}
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    return batch
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = []
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                try:
+                    rows.append((float(parts[0]), float(parts[1]), parts[3:7]))
+                except ValueError:
+                    pass
+        os.unlink(self.path)
+        if rows:
+            sm = sorted(r[0] for r in rows)
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = rows[0][1]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = [n for i, n in enumerate(names) if any(r[2][i].lower().startswith("active") for r in rows)]
+            out["samples"] = len(rows)
+        return out
+
+
+# ====================================================================================== our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from vae_gslm_b200 import _lib, ops
+    from vae_gslm_b200.arena import ParamArena
+    from vae_gslm_b200.dp import GradReducer
+    from vae_gslm_b200.hparams.hp import Hparams
+    from vae_gslm_b200.models.speech.lvtr import LVTR
+    from vae_gslm_b200.trainers.speech.lvtr import assemble_loss
+    from vae_gslm_b200.training_lib.trainer import init_weights
+    from vae_gslm_b200.utils.tensormask import TensorMask
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py measures the CUDA path: no GPU visible (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torchrun)"
+    _lib.load()
+
+    B, T = args.batch, args.frames
+    torch.manual_seed(0)                                    # identical weights on every rank
+    hp = Hparams.from_yamlfile(CFG)
+    model = LVTR(hp.model, input_dim=N_MELS)
+    model.apply(init_weights)
+    model = model.to(dev).set_compute_dtype(torch.bfloat16)
+    arena = ParamArena(model, weight_decay=hp.training.optimizer.weight_decay)
+    reducer = GradReducer(arena, bucket_bytes=64 << 20)
+    lr = hp.training.optimizer.lr
+
+    host = synthetic_batch(B, T, rank, pin=True)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step(batch, from_host):
+        if from_host:
+            batch = {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
+        arena.zero_grad()
+        reducer.prepare(last_micro_batch=True)
+        out = model(TensorMask(batch["x"], batch["mask"]), utterance=TensorMask(batch["utterance"], batch["utt_mask"]))
+        terms = assemble_loss(out, kld_weight=KW)
+        terms["loss"].backward()
+        reducer.finish()
+        arena.adamw_step(lr)
+        if from_host:
+            return float(terms["loss"].item())              # device→host read of the step's result
+        return terms["loss"]
+
+    def timed(nsteps, from_host):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(nsteps):
+            last = step(host if from_host else resident, from_host)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), last
+
+    for _ in range(args.warmup):
+        step(resident, False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count
+    ms, last_loss = timed(args.steps, False)
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop()
+    ms_e2e, loss_host = timed(args.steps, True)
+
+    frames_per_step = B * T * world
+    value = frames_per_step * args.steps / (ms / 1e3)
+    e2e_value = frames_per_step * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel (gemm_tc_kernel): one extra, instrumented step (not part of the timing)
+    ops.PROFILE = []
+    step(resident, False)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in prof)
+    gemm_flops = sum(f for _, _, f, _ in prof)
+    peaks = measured_peaks()
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    step_ms = ms / args.steps
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all instances of one step)",
+                "achieved": round(achieved, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": round(achieved / peaks["bf16_sustained"], 4), "peak_source": peaks["src"] + " sustained",
+                "traffic": None, "launches_per_step": len(prof), "gemm_ms_per_step": round(gemm_ms, 3),
+                "share_of_step": round(gemm_ms / step_ms, 3)}
+
+    result = {
+        "metric": "train_mel_frames_per_sec", "value": round(value, 1), "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"VAE-GSLM bf16 training step (fwd+bwd+allreduce+AdamW), {T / 50:.0f} s segments",
+                   "per_gpu_batch": B, "frames_per_seq": T, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "params": 226_957_564, "l2": "working set (454 MB bf16 weights + activations) exceeds the 126 MB L2",
+                   "init": "random (reference init rules)"},
+        "per_gpu_frames_per_sec": round(value / world, 1),
+        "model_tflops_per_gpu": round(train_flops_per_frame(T) * value / world / 1e12, 1),
+        "mfu_vs_measured_sustained": round(train_flops_per_frame(T) * value / world / 1e12 / peaks["bf16_sustained"], 4),
+        "mfu_vs_nominal_2250": round(train_flops_per_frame(T) * value / world / 1e12 / 2250.0, 4),
+        "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": loss_host},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "loss": float(last_loss),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        result["cpu_baseline"] = cpu_baseline_sample(model, hp)
+    if rank == 0 and not args.no_decode:
+        result["decode"] = decode_bench(model, dev, peaks)
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def decode_bench(model, dev, peaks, batches=(1, 64), prompt=150, steps=48):
+    """cached generation (configs[2]): 3 s prompt, prefill then `steps` single-token steps; frames/s and the HBM
+    roofline of SURVEY §8d: bytes(B,Tk) = 408.7 MB weights + B·65,536·(Tk+1)."""
+    from vae_gslm_b200.utils.tensormask import TensorMask
+    out = {}
+    model.eval()
+    for B in batches:
+        g = torch.Generator().manual_seed(7)
+        prior = torch.cat([torch.randint(0, VOCAB, (B, prompt, 1), generator=g).float(),
+                           torch.randn(B, prompt, 4, generator=g)], -1).to(dev)
+        model.transformer[0].cache_len_hint = prompt + 1 + steps + 8
+        o = model.step(prior, past_kv=None, temperature=0.85, token_temperature=0.85, push_init_state=True)
+        state, kv = o["output"][:, -1:], o["kv"]
+        for _ in range(4):
+            o = model.step(state, past_kv=kv, temperature=0.85, token_temperature=0.85)
+            state, kv = o["output"], o["kv"]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            o = model.step(state, past_kv=kv, temperature=0.85, token_temperature=0.85)
+            state, kv = o["output"], o["kv"]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        tk = prompt + 1 + 4 + steps // 2
+        bytes_step = 408.7e6 + B * 65536 * (tk + 1)
+        roof = B * peaks["hbm_gbs"] * 1e9 / bytes_step
+        out[f"B{B}"] = {"frames_per_sec": round(B / (ms / 1e3), 1), "ms_per_step": round(ms, 3),
+                        "hbm_roofline_frames_per_sec": round(roof, 1), "frac": round(B / (ms / 1e3) / roof, 4),
+                        "mean_tk": tk, "mode": "eager python loop (no CUDA graph)"}
+    return out
+
+
+# ====================================================================================== CPU baseline / reference arm
+def _oracle_state(model_or_none, hp):
+    from vae_gslm_b200.models.speech.lvtr import LVTR
+    from vae_gslm_b200.training_lib.trainer import init_weights
+    if model_or_none is None:
+        torch.manual_seed(0)
+        model_or_none = LVTR(hp.model, input_dim=N_MELS)
+        model_or_none.apply(init_weights)
+    names = {n for n, _ in model_or_none.named_parameters()}
+    return {k: v.detach().float().cpu().clone().requires_grad_(k in names) for k, v in model_or_none.state_dict().items()}
+
+
+def _oracle_step(sd, cfg, batch, rng, opt=None):
+    from oracle import lvtr_oracle as O
+    out = O.lvtr_forward(sd, cfg, batch["x"], batch["mask"], batch["utterance"], batch["utt_mask"], rng)
+    loss = O.total_loss(out, KW)
+    for v in sd.values():
+        v.grad = None
+    loss.backward()
+    if opt is not None:
+        opt.step()
+    return float(loss.detach())
+
+
+def _rng(B, T, seed=4321):
+    g = torch.Generator().manual_seed(seed)
+    return {"eps_q": torch.randn(B, T, 4, generator=g), "init_state": torch.rand(B, 1, 64, generator=g) * 2 - 1,
+            "eps_p": torch.randn(B, T, 4, generator=g), "diff_t": torch.randint(0, 1000, (B,), generator=g),
+            "diff_noise": torch.randn(B, T, N_MELS, generator=g)}
+
+
+def cpu_baseline_sample(model, hp, B=2, T=1000):
+    """the oracle (reference algorithm, plain torch fp32) on the box's host cores, one bounded sample."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = _oracle_state(model, hp)
+    cfg = hp.model.to_dict()
+    _oracle_step(sd, cfg, synthetic_batch(1, 64, 0), _rng(1, 64))          # warm-up (allocator, thread pools)
+    batch, rng = synthetic_batch(B, T, 0), _rng(B, T)
+    t0 = time.perf_counter()
+    _oracle_step(sd, cfg, batch, rng)
+    dt = time.perf_counter() - t0
+    return {"value": round(B * T / dt, 1), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 fwd+bwd of the oracle (fp32, torch CPU) at B={B}, T={T}: {dt:.1f} s",
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from vae_gslm_b200.hparams.hp import Hparams
+    torch.set_num_threads(os.cpu_count() or 1)
+    hp = Hparams.from_yamlfile(CFG)
+    sd = _oracle_state(None, hp)
+    cfg = hp.model.to_dict()
+    B, T = 1, args.frames                                  # bounded sample of the workload per step
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.AdamW([{"params": [p for p in params if p.ndim != 1]},
+                             {"params": [p for p in params if p.ndim == 1], "weight_decay": 0.0}],
+                            lr=hp.training.optimizer.lr, betas=(0.9, 0.98), weight_decay=0.1)
+    batch, rng = synthetic_batch(B, T, 0), _rng(B, T)
+    for _ in range(args.warmup):
+        _oracle_step(sd, cfg, batch, rng, opt)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = _oracle_step(sd, cfg, batch, rng, opt)
+    dt = time.perf_counter() - t0
+    value = B * T * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "train_mel_frames_per_sec", "value": round(value, 1), "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"VAE-GSLM training step (fwd+bwd+AdamW), {T / 50:.0f} s segments — reference algorithm "
+                               "(oracle port of the PyTorch modules) on host cores", "per_step_sample": f"B={B}, T={T}",
+                   "frames_per_seq": T, "parallelism": "cpu"},
+        "cpu_baseline": {"value": round(value, 1), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} steps of B={B}, T={T} (fwd+bwd+AdamW), fp32"},
+        "e2e": {"value": round(value, 1), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss": loss}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="sequences per GPU (repo config: 8)")
+    ap.add_argument("--frames", type=int, default=1000, help="frames per sequence (20 s segments at 50 Hz)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

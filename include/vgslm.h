@@ -259,7 +259,10 @@ int vg_sample_token(const void* logits, int64_t ld, const float* u /* nullable â
 int vg_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                   void* shadow_bf16 /* nullable */, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, float bias_corr1, float bias_corr2,
-                  float grad_scale, vg_stream_t stream);
+                  float grad_scale,
+                  const float* hyper_dev /* nullable: device {lr, 1/bc1, 1/sqrt(bc2), 1-lr*wd} overriding the
+                                            scalar arguments, so a captured CUDA graph can be replayed */,
+                  vg_stream_t stream);
 int vg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vg_stream_t stream);
 
 #ifdef __cplusplus

@@ -282,6 +282,6 @@ def test_adamw_matches_torch():
         ref.grad = g.clone()
         opt.step()
         L.call("vg_adamw_step", L.ptr(arena), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(shadow), n, 5e-4, 0.9, 0.98, 1e-8,
-               0.1, 1 - 0.9 ** step, 1 - 0.98 ** step, 1.0, L.stream())
+               0.1, 1 - 0.9 ** step, 1 - 0.98 ** step, 1.0, None, L.stream())
     assert rel_err(arena, ref.detach()) < 1e-6
     assert torch.equal(shadow, arena.to(torch.bfloat16))

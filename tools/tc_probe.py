@@ -37,7 +37,7 @@ def run(tag, M, N, K, ta, tb, out_dtype=torch.float32):
 
 
 ok = True
-for (M, N, K) in [(128, 128, 64), (128, 256, 64), (128, 128, 256), (256, 512, 128), (300, 200, 72)]:
+for (M, N, K) in [(128, 128, 64), (128, 256, 64), (128, 128, 256), (256, 512, 128), (304, 200, 72)]:
     for ta, tb in [(False, True), (False, False), (True, True), (True, False)]:
         ok &= run("probe", M, N, K, ta, tb)
 ok &= run("big", 5120, 4096, 1024, False, True, torch.bfloat16)

@@ -128,12 +128,14 @@ _SIGNATURES = {
     "vg_masked_l1_fwd": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _p, _sz, _p]),
     "vg_masked_l1_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
     "vg_sample_token": (C.c_int, [_p, _i64, _p, _f32, _p, _i64, _i64, C.c_int, _p]),
-    "vg_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _p]),
+    "vg_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _p, _p]),
     "vg_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
 }
 
 _lib: Optional[C.CDLL] = None
-launch_count = 0   # kernels-launching C-ABI calls issued by this process (bench.py reports it)
+launch_count = 0   # kernels of libvgslm launched by this process (bench.py reports it)
+_KERNELS_PER_CALL = {"vg_rmsnorm_bwd": 2, "vg_colsum": 2, "vg_attn_bwd": 3, "vg_latent_front_bwd": 3,
+                     "vg_latent_back_fwd": 2, "vg_latent_back_bwd": 2, "vg_softmax_ce_fwd": 2, "vg_masked_l1_fwd": 2}
 
 
 def load() -> C.CDLL:
@@ -174,7 +176,7 @@ def call(name: str, *args) -> None:
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"libvgslm {name} failed (rc={rc}): {last_error()}")
-    launch_count += 1
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
 
 
 def dtype_id(dt: torch.dtype) -> int:

@@ -1,0 +1,172 @@
+"""Flat parameter / gradient / optimizer-state arenas (B200-first memory layout for the training step).
+
+All parameters of the model are re-pointed at views of two contiguous fp32 buffers (weight-decayed
+tensors | 1-D tensors, the split of training_lib/optimizer.py:110-125), in forward execution order.
+Gradients, AdamW moments and the bf16 shadow weights mirror that layout, so that
+
+  * the optimizer is TWO launches of the fused AdamW kernel (which also refreshes the bf16 shadows),
+    instead of torch's multi-tensor AdamW + 100 cast kernels;
+  * data-parallel gradient buckets are contiguous slices (no flatten/unflatten copies) that become
+    ready in roughly reverse order during backward (dp.py);
+  * the wgrad GEMMs of the big transformer matrices write straight into the gradient arena
+    (``param._vg_main_grad``) instead of going through autograd's accumulate pass.
+
+state_dict() / load_state_dict() keep working: parameters are ordinary nn.Parameters whose storage
+happens to live in the arena.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+_ALIGN = 64      # elements; keeps every tensor 256-byte aligned inside the arena (TMA needs 16 B)
+
+
+def execution_order(model: nn.Module) -> List[Tuple[str, nn.Parameter]]:
+    """parameters in (approximate) forward execution order, so that backward completes buckets back to front."""
+    prefixes = ["encoder.", "token_embedding.", "token_fuser.", "transformer.0.", "q_spliter.", "token_spliter.",
+                "transformer.1.", "transformer_flow.", "token_predictor.", "utterance_encoder.", "decoder."]
+    named = list(model.named_parameters())
+    out, seen = [], set()
+    for pre in prefixes:
+        for n, p in named:
+            if n.startswith(pre) and n not in seen:
+                out.append((n, p))
+                seen.add(n)
+    out += [(n, p) for n, p in named if n not in seen]
+    return out
+
+
+class _Group:
+    """one contiguous arena: params, grads, exp_avg, exp_avg_sq (+ optional bf16 shadow)."""
+
+    def __init__(self, items: List[Tuple[str, nn.Parameter]], device, weight_decay: float, shadow: bool):
+        self.names = [n for n, _ in items]
+        self.params = [p for _, p in items]
+        self.weight_decay = weight_decay
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = max(off, _ALIGN)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.p = torch.zeros(self.numel, **f32)
+        self.g = torch.zeros(self.numel, **f32)
+        self.m = torch.zeros(self.numel, **f32)
+        self.v = torch.zeros(self.numel, **f32)
+        self.shadow = torch.zeros(self.numel, dtype=torch.bfloat16, device=device) if shadow else None
+        for p, o in zip(self.params, self.offsets):
+            n = p.numel()
+            self.p[o:o + n].copy_(p.detach().reshape(-1))
+            p.data = self.p[o:o + n].view(p.shape)
+            p.grad = self.g[o:o + n].view(p.shape)
+            if shadow and p.dim() == 2:
+                p._vg_shadow = self.shadow[o:o + n].view(p.shape)
+        if shadow:
+            L.call("vg_cast_f32_to_bf16", L.ptr(self.p), L.ptr(self.shadow), self.numel, L.stream())
+
+    def slice_of(self, index: int) -> Tuple[int, int]:
+        return self.offsets[index], self.params[index].numel()
+
+
+class ParamArena:
+    def __init__(self, model: nn.Module, weight_decay: float = 0.1, bf16_shadow: bool = True,
+                 direct_wgrad: bool = True) -> None:
+        device = next(model.parameters()).device
+        items = execution_order(model)
+        self.decay = _Group([(n, p) for n, p in items if p.ndim != 1], device, weight_decay, bf16_shadow)
+        self.nodecay = _Group([(n, p) for n, p in items if p.ndim == 1], device, 0.0, False)
+        self.groups = [self.decay, self.nodecay]
+        self.step_count = 0
+        self.micro_batch = 0          # index inside the current accumulation window (0 → wgrad overwrites)
+        self.hyper = [torch.zeros(4, dtype=torch.float32, device=device) for _ in self.groups]
+        self._hyper_host = [torch.zeros(4, dtype=torch.float32).pin_memory() if torch.cuda.is_available()
+                            else torch.zeros(4) for _ in self.groups]
+        self.on_grad_ready = None     # dp.py installs a callback(param) here
+        # big transformer matrices: their wgrad GEMM writes the arena directly (ops._Linear / ops._FFN)
+        self.direct: List[nn.Parameter] = []
+        if direct_wgrad:
+            for n, p in zip(self.decay.names, self.decay.params):
+                if n.startswith("transformer.0.layers.") and p.dim() == 2 or n == "transformer.0.linear.weight":
+                    p._vg_main_grad = p.grad
+                    p._vg_arena = self
+                    self.direct.append(p)
+        direct_ids = {id(p) for p in self.direct}
+        # contiguous runs of NON-direct gradients: only those need zeroing before backward
+        self._zero_runs: List[torch.Tensor] = []
+        for grp in self.groups:
+            run_start = None
+            for i, p in enumerate(grp.params):
+                o, n = grp.slice_of(i)
+                end = grp.offsets[i + 1] if i + 1 < len(grp.params) else grp.numel
+                if id(p) in direct_ids:
+                    if run_start is not None:
+                        self._zero_runs.append(grp.g[run_start:o])
+                        run_start = None
+                elif run_start is None:
+                    run_start = o
+                if i + 1 == len(grp.params) and run_start is not None:
+                    self._zero_runs.append(grp.g[run_start:end])
+
+    # ------------------------------------------------------------------ per-step protocol
+    def zero_grad(self) -> None:
+        """gradients the autograd engine accumulates into are zeroed; direct-wgrad slices are overwritten (beta=0)."""
+        for run in self._zero_runs:
+            run.zero_()
+        self.micro_batch = 0
+
+    def wgrad_beta(self) -> float:
+        return 0.0 if self.micro_batch == 0 else 1.0
+
+    def end_micro_batch(self) -> None:
+        self.micro_batch += 1
+
+    def grad_ready(self, param: nn.Parameter) -> None:
+        if self.on_grad_ready is not None:
+            self.on_grad_ready(param)
+
+    def adamw_step(self, lr: float, beta1: float = 0.9, beta2: float = 0.98, eps: float = 1e-8,
+                   grad_scale: float = 1.0, use_device_hyper: bool = False) -> None:
+        """torch.optim.AdamW semantics over both arenas; refreshes the bf16 shadows in the same pass."""
+        self.step_count += 1
+        bc1 = 1.0 - beta1 ** self.step_count
+        bc2 = 1.0 - beta2 ** self.step_count
+        for grp, hyper, host in zip(self.groups, self.hyper, self._hyper_host):
+            hp = None
+            if use_device_hyper:
+                host[0], host[1], host[2], host[3] = lr, 1.0 / bc1, bc2 ** -0.5, 1.0 - lr * grp.weight_decay
+                hyper.copy_(host, non_blocking=True)
+                hp = L.ptr(hyper)
+            L.call("vg_adamw_step", L.ptr(grp.p), L.ptr(grp.g), L.ptr(grp.m), L.ptr(grp.v),
+                   L.ptr(grp.shadow) if grp.shadow is not None else None, grp.numel, lr, beta1, beta2, eps,
+                   grp.weight_decay, bc1, bc2, grad_scale, hp, L.stream())
+
+    # ------------------------------------------------------------------ data-parallel buckets
+    def buckets(self, bucket_bytes: int = 64 << 20) -> List[Tuple[torch.Tensor, List[nn.Parameter]]]:
+        """contiguous gradient slices of ~bucket_bytes with the parameters they hold, in arena order."""
+        out = []
+        for grp in self.groups:
+            start, members = 0, []
+            for i, p in enumerate(grp.params):
+                end = grp.offsets[i + 1] if i + 1 < len(grp.params) else grp.numel
+                members.append(p)
+                if (end - start) * 4 >= bucket_bytes or i + 1 == len(grp.params):
+                    out.append((grp.g[start:end], members))
+                    start, members = end, []
+        return out
+
+    def total_numel(self) -> int:
+        return sum(g.numel for g in self.groups)
+
+
+def cosine_lr(step: int, base_lr: float, min_lr: float, flat_steps: int, total_steps: int) -> float:
+    """training_lib/optimizer.py:58-107 for the VAE-GSLM recipe: flat for `flat_steps`, then cosine to min_lr."""
+    import math
+    if step < flat_steps:
+        return base_lr
+    t, tmax = step - flat_steps, max(1, total_steps - flat_steps)
+    return min_lr + (base_lr - min_lr) * (1 + math.cos(math.pi * min(t, tmax) / tmax)) / 2

@@ -47,16 +47,25 @@ attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __rest
 #pragma unroll
   for (int d = 0; d < 8; ++d) acc[d] = 0.f;
 
-  for (int j = j_begin + grp; j < j_end; j += DEC_GROUPS) {
+  // the trip count is CTA-uniform and out-of-range key groups are predicated: the 8-lane shuffles below use the
+  // full-warp mask, so every lane of a warp must reach them together
+  for (int base = j_begin; base < j_end; base += DEC_GROUPS) {
+    const int j = base + grp;
+    const bool active = j < j_end;
     Vec8<T> kv8, vv8;
-    if (j == pos) {
-      kv8.load(knew + sub * 8);
-      vv8.load(vnew + sub * 8);
-      kv8.store(kc + (int64_t)pos * DD + sub * 8);      // append (fused kv-cache write)
-      vv8.store(vc + (int64_t)pos * DD + sub * 8);
+    if (active) {
+      if (j == pos) {
+        kv8.load(knew + sub * 8);
+        vv8.load(vnew + sub * 8);
+        kv8.store(kc + (int64_t)pos * DD + sub * 8);      // append (fused kv-cache write)
+        vv8.store(vc + (int64_t)pos * DD + sub * 8);
+      } else {
+        kv8.load(kc + (int64_t)j * DD + sub * 8);
+        vv8.load(vc + (int64_t)j * DD + sub * 8);
+      }
     } else {
-      kv8.load(kc + (int64_t)j * DD + sub * 8);
-      vv8.load(vc + (int64_t)j * DD + sub * 8);
+#pragma unroll
+      for (int d = 0; d < 8; ++d) { kv8.v[d] = 0.f; vv8.v[d] = 0.f; }
     }
     float s = 0.f;
 #pragma unroll
@@ -64,14 +73,16 @@ attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __rest
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s = s * scale - slope * (float)(pos - j);
-    const float mnew = fmaxf(m, s);
-    const float corr = expf(m - mnew);      // m = -inf on first key → 0
-    const float p = expf(s - mnew);
-    l = l * corr + p;
+    if (active) {
+      s = s * scale - slope * (float)(pos - j);
+      const float mnew = fmaxf(m, s);
+      const float corr = expf(m - mnew);      // m = -inf on first key → 0
+      const float p = expf(s - mnew);
+      l = l * corr + p;
 #pragma unroll
-    for (int d = 0; d < 8; ++d) acc[d] = acc[d] * corr + p * vv8.v[d];
-    m = mnew;
+      for (int d = 0; d < 8; ++d) acc[d] = acc[d] * corr + p * vv8.v[d];
+      m = mnew;
+    }
   }
   if (sub == 0) { sm_m[grp] = m; sm_l[grp] = l; }
 #pragma unroll

@@ -9,9 +9,13 @@ namespace vg {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ shadow, int64_t n, float lr, float beta1, float beta2, float eps,
-             float decay_mul, float inv_bc1, float inv_sqrt_bc2, float grad_scale) {
+             float decay_mul, float inv_bc1, float inv_sqrt_bc2, float grad_scale,
+             const float* __restrict__ hyper) {
   const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
+  if (hyper) {   // device-resident {lr, 1/bias_corr1, 1/sqrt(bias_corr2), 1 - lr*wd}: graph replays see new values
+    lr = hyper[0]; inv_bc1 = hyper[1]; inv_sqrt_bc2 = hyper[2]; decay_mul = hyper[3];
+  }
   if (i4 + 4 <= n) {
     float4 pv = *reinterpret_cast<float4*>(p + i4);
     const float4 gv = *reinterpret_cast<const float4*>(g + i4);
@@ -73,7 +77,8 @@ using namespace vg;
 
 extern "C" int vg_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
                              int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                             float bias_corr1, float bias_corr2, float grad_scale, vg_stream_t stream) {
+                             float bias_corr1, float bias_corr2, float grad_scale, const float* hyper_dev,
+                             vg_stream_t stream) {
   VG_REQUIRE(param && grad && exp_avg && exp_avg_sq, -1, "vg_adamw_step: null pointer");
   VG_REQUIRE(n > 0, -3, "vg_adamw_step: n must be positive");
   VG_REQUIRE(aligned(param, 16) && aligned(grad, 16) && aligned(exp_avg, 16) && aligned(exp_avg_sq, 16) &&
@@ -82,7 +87,7 @@ extern "C" int vg_adamw_step(float* param, const float* grad, float* exp_avg, fl
   const int64_t nthreads = ceil_div(n, 4);
   adamw_kernel<<<(unsigned)ceil_div(nthreads, 256), 256, 0, (cudaStream_t)stream>>>(
       param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr, beta1, beta2, eps,
-      1.f - lr * weight_decay, 1.f / bias_corr1, 1.f / sqrtf(bias_corr2), grad_scale);
+      1.f - lr * weight_decay, 1.f / bias_corr1, 1.f / sqrtf(bias_corr2), grad_scale, hyper_dev);
   VG_LAUNCH_CHECK("vg_adamw_step");
   return 0;
 }

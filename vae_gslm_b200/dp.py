@@ -1,0 +1,93 @@
+"""Data-parallel gradient all-reduce for the VAE-GSLM training step.
+
+The reference trains with Lightning's ``ddp`` strategy (scripts/train.py:93-95): DistributedDataParallel,
+25 MB buckets, gradient MEAN across ranks, fired on every micro-batch.  Here (one process per GPU, NCCL over
+NVLink/NVSwitch through torch.distributed) the buckets are contiguous slices of the ParamArena gradient
+buffer (no flatten copies); a bucket is all-reduced on a side stream as soon as backward has produced all
+of its gradients, overlapping the rest of backward; and the collective only runs on the last micro-batch
+of an accumulation window.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .arena import ParamArena
+
+
+class GradReducer:
+    def __init__(self, arena: ParamArena, bucket_bytes: int = 64 << 20, process_group=None,
+                 overlap: bool = True) -> None:
+        self.arena = arena
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.buckets = arena.buckets(bucket_bytes)
+        self.overlap = overlap
+        self._bucket_of: Dict[int, int] = {}
+        self._pending: List[int] = []
+        self._size: List[int] = []
+        for bi, (_, members) in enumerate(self.buckets):
+            self._size.append(len(members))
+            for p in members:
+                self._bucket_of[id(p)] = bi
+        self._handles = []
+        self.enabled = False           # armed only for the micro-batch that closes an accumulation window
+        self.is_cuda = self.buckets[0][0].is_cuda
+        self.comm_stream = torch.cuda.Stream() if self.is_cuda else None
+        self._launched: List[bool] = []
+        direct = {id(p) for p in arena.direct}
+        for _, members in self.buckets:
+            for p in members:
+                if id(p) not in direct:       # autograd-accumulated gradients announce themselves through a hook
+                    p.register_post_accumulate_grad_hook(self._hook)
+        arena.on_grad_ready = self._ready     # direct-wgrad parameters are announced by ops._wgrad
+
+    # ------------------------------------------------------------------ per-backward protocol
+    def prepare(self, last_micro_batch: bool = True) -> None:
+        self.enabled = last_micro_batch and self.world > 1
+        self._pending = list(self._size)
+        self._launched = [False] * len(self.buckets)
+        self._handles = []
+
+    def _hook(self, param) -> None:
+        self._ready(param)
+
+    def _ready(self, param) -> None:
+        if not self.enabled:
+            return
+        bi = self._bucket_of.get(id(param))
+        if bi is None:
+            return
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and self.overlap:
+            self._launch(bi)
+
+    def _launch(self, bi: int) -> None:
+        if self._launched[bi]:
+            return
+        self._launched[bi] = True
+        flat = self.buckets[bi][0]
+        if self.is_cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:       # gloo (CPU tests): no AVG op
+            h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._handles.append((h, flat))
+
+    def finish(self) -> None:
+        """reduce whatever has not been launched yet (parameters unused in this step never fire a hook) and make
+        the compute stream wait for the collectives."""
+        if not self.enabled:
+            return
+        for bi in range(len(self.buckets)):
+            self._launch(bi)
+        if self.is_cuda:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            for h, flat in self._handles:
+                h.wait()
+                flat.div_(self.world)
+        self.enabled = False

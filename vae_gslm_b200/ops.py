@@ -16,6 +16,8 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN
 
 # GEMM backend used for bf16 operands: AUTO picks tcgen05 when the shape qualifies.
 GEMM_BACKEND = GEMM_AUTO
+# when a list, every bf16 GEMM launch appends (start_event, end_event, flops, dtype) — bench.py's roofline probe
+PROFILE = None
 
 ACT_IDS = {"none": ACT_NONE, None: ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU,
            "ReLU": ACT_RELU, "GELU": ACT_GELU}
@@ -113,7 +115,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
     g.mask_before_residual = int(mask_first)
     g.beta = beta
     be = GEMM_BACKEND if backend is None else backend
+    prof = PROFILE if (PROFILE is not None and a.dtype == torch.bfloat16) else None
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.call("vg_gemm", C.byref(g), be, None, 0, L.stream())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K, a.dtype))
     return out
 
 
@@ -197,6 +206,19 @@ def rmsnorm(x: torch.Tensor, scale: torch.Tensor, eps: float, mask: Optional[tor
 
 
 # ----------------------------------------------------------------------------------------- Linear
+def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor) -> Optional[torch.Tensor]:
+    """dW = dyᵀ·x in fp32.  Parameters that live in a ParamArena (arena.py) get the GEMM written straight into
+    their gradient slice (beta = 1 on later micro-batches) and autograd receives None."""
+    main = getattr(weight, "_vg_main_grad", None)
+    if main is not None:
+        arena = weight._vg_arena
+        gemm(dy2, x2, trans_a=True, trans_b=False, out=main, beta=arena.wgrad_beta())
+        arena.grad_ready(weight)
+        return None
+    dw = gemm(dy2, x2, trans_a=True, trans_b=False, out_dtype=torch.float32)
+    return dw if weight.dtype == torch.float32 else dw.to(weight.dtype)
+
+
 class _Linear(torch.autograd.Function):
     """y = mask/residual epilogue(act(x·Wᵀ + b)) — one GEMM launch; backward = dgrad + wgrad (+ colsum)."""
 
@@ -213,14 +235,14 @@ class _Linear(torch.autograd.Function):
         y = gemm(x2, w, trans_b=True, out_dtype=odt, bias=b, act=act, preact=pre, residual=res2,
                  row_mask=mask_u8, mask_first=mask_first)
         ctx.save_for_backward(x2, w, pre if need_pre else (y if act != ACT_NONE else None), mask_u8)
-        ctx.meta = (act, mask_first, x.shape, weight.dtype, bias is not None, residual is not None,
+        ctx.meta = (act, mask_first, x.shape, weight, bias is not None, residual is not None,
                     residual.shape if residual is not None else None)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, dy):
         x2, w, act_src, mask_u8 = ctx.saved_tensors
-        act, mask_first, xshape, wdtype, has_bias, has_res, res_shape = ctx.meta
+        act, mask_first, xshape, weight, has_bias, has_res, res_shape = ctx.meta
         dy2 = _rows2d(dy).contiguous()
         g = mask_rows_(dy2, mask_u8) if mask_u8 is not None else dy2
         dres = None
@@ -233,9 +255,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(dpre, w, trans_b=False).view(xshape)
         if ctx.needs_input_grad[1]:
-            dw = gemm(dpre, x2, trans_a=True, trans_b=False, out_dtype=torch.float32)
-            if wdtype != torch.float32:
-                dw = dw.to(wdtype)
+            dw = _wgrad(dpre, x2, weight)
         if has_bias and ctx.needs_input_grad[2]:
             db = colsum(dpre)
         return dx, dw, db, dres, None, None, None, None, None
@@ -266,21 +286,21 @@ class _FFN(torch.autograd.Function):
         y = gemm(h, w2c, trans_b=True, bias=b2.detach().float() if b2 is not None else None, residual=res2,
                  row_mask=mask_u8)
         ctx.save_for_backward(x2, w1c, w2c, pre, h, mask_u8)
-        ctx.meta = (act, x.shape, b1 is not None, b2 is not None, residual is not None)
+        ctx.meta = (act, x.shape, b1 is not None, b2 is not None, residual is not None, w1, w2)
         return y.view(x.shape[:-1] + (w2c.shape[0],))
 
     @staticmethod
     def backward(ctx, dy):
         x2, w1c, w2c, pre, h, mask_u8 = ctx.saved_tensors
-        act, xshape, has_b1, has_b2, has_res = ctx.meta
+        act, xshape, has_b1, has_b2, has_res, w1, w2 = ctx.meta
         dy2 = _rows2d(dy).contiguous()
         g = mask_rows_(dy2, mask_u8) if mask_u8 is not None else dy2
         dres = g.view(dy.shape) if has_res and ctx.needs_input_grad[5] else None
         dpre = gemm(g, w2c, trans_b=False, dact_src=pre, dact=act)            # (g·W2) ⊙ act'(pre)
-        dw2 = gemm(g, h, trans_a=True, trans_b=False, out_dtype=torch.float32) if ctx.needs_input_grad[3] else None
+        dw2 = _wgrad(g, h, w2) if ctx.needs_input_grad[3] else None
         db2 = colsum(g) if has_b2 and ctx.needs_input_grad[4] else None
         dx = gemm(dpre, w1c, trans_b=False).view(xshape) if ctx.needs_input_grad[0] else None
-        dw1 = gemm(dpre, x2, trans_a=True, trans_b=False, out_dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        dw1 = _wgrad(dpre, x2, w1) if ctx.needs_input_grad[1] else None
         db1 = colsum(dpre) if has_b1 and ctx.needs_input_grad[2] else None
         return dx, dw1, db1, dw2, db2, dres, None, None
 
