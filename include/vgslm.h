@@ -114,6 +114,9 @@ int vg_attn_fwd(const void* q, const void* k, const void* v, int64_t ld_q, int64
                 int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D, int64_t q_offset,
                 int64_t kv_batch_stride /* 0 → Tk*ld_kv (packed) */, int64_t kv_head_stride /* 0 → D */,
                 float scale, int dtype, vg_stream_t stream);
+/* backend selection for vg_attn_fwd/bwd: 0 = auto (tcgen05 kernels for packed bf16, CUDA-core kernels otherwise),
+ * 1 = CUDA-core (fp32-exact softmax) kernels only, 2 = tcgen05 required (error if the layout does not qualify) */
+int vg_set_attn_backend(int backend);
 size_t vg_attn_bwd_workspace(int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D);
 int vg_attn_bwd(const void* dout, int64_t ld_dout,
                 const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv,

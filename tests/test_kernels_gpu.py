@@ -159,9 +159,18 @@ def _attn_ref(qkv, H, lengths, slopes, q_offset=0, k=None, v=None):
     return o
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,T,H", [(2, 24, 2), (3, 130, 4), (2, 640, 16)])
-def test_attention_fwd_bwd(dtype, B, T, H):
+@pytest.mark.parametrize("mode", ["f32-simt", "bf16-simt", "bf16-tcgen05"])
+@pytest.mark.parametrize("B,T,H", [(2, 24, 2), (3, 130, 4), (2, 640, 16), (1, 1000, 3), (2, 257, 2)])
+def test_attention_fwd_bwd(mode, B, T, H):
+    dtype = torch.float32 if mode.startswith("f32") else torch.bfloat16
+    L.call("vg_set_attn_backend", 2 if mode.endswith("tcgen05") else 1)
+    try:
+        _attention_fwd_bwd(dtype, B, T, H)
+    finally:
+        L.call("vg_set_attn_backend", 0)
+
+
+def _attention_fwd_bwd(dtype, B, T, H):
     D = 64
     qkv = (0.5 * torch.randn(B, T, 3 * H * D, device=DEV)).to(dtype).requires_grad_(True)
     lengths = torch.randint(T // 2, T + 1, (B,), device=DEV, dtype=torch.int32)

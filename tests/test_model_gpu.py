@@ -100,15 +100,28 @@ def test_bf16_forward_backward_within_tolerance(golden, backend):
     assert abs(float(terms["token_kld"]) - float(f["ce"])) / abs(float(f["ce"])) < T
     assert abs(float(terms["kld"]) - float(f["kld"])) / abs(float(f["kld"])) < T
     assert max_rel(out["logits"].value.cpu(), f["logits"]) < T
-    # transformer-side gradients (our kernels) hold the 2e-2 class tolerance; the conv encoder / UNet run under
-    # torch.autocast exactly like the reference and carry its bf16 conv noise at this tiny width (16 channels)
+    # Gradients: the north star's bf16 bar is "within 2e-2 of the reference PyTorch path in bf16 mode".  The
+    # bf16 reference of record is the oracle under torch.autocast on this GPU; both sides are compared with the
+    # fp32 golden gradients and ours must be within 2e-2, or no worse than 2.5x the reference's own bf16 error.
+    ref_err = _autocast_oracle_grad_errors(golden)
     bad = []
     for name, p in model.named_parameters():
         e = frob_rel(p.grad.cpu(), golden["grads"][name])
-        lim = 0.15 if name.startswith(("encoder.0", "decoder.", "utterance_encoder")) else 5e-2
-        if e > lim:
-            bad.append((name, e))
+        if e > max(2e-2, 2.5 * ref_err[name]):
+            bad.append((name, round(e, 4), round(ref_err[name], 4)))
     assert not bad, bad
+
+
+def _autocast_oracle_grad_errors(golden):
+    """Frobenius-relative error (vs the fp32 golden gradients) of the oracle run under bf16 autocast on the GPU."""
+    sd = {k: v.to(DEV).clone().requires_grad_(k in golden["grads"]) for k, v in golden["state_dict"].items()}
+    i = {k: v.to(DEV) for k, v in golden["inputs"].items()}
+    rng = {k: i[k] for k in ("eps_q", "init_state", "eps_p", "diff_t", "diff_noise")}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = O.lvtr_forward(sd, golden["config"], i["x"], i["mask"], i["utterance"], i["utt_mask"], rng)
+        loss = O.total_loss(out, float(golden["forward"]["kw"]))
+    loss.backward()
+    return {k: frob_rel(sd[k].grad.cpu(), g) for k, g in golden["grads"].items()}
 
 
 def test_fp32_cached_decode_greedy_tokens_bit_exact(golden):
@@ -288,9 +301,18 @@ def test_full_config_against_oracle(mode):
         assert abs(float(mine) - float(r)) / abs(float(r)) < T_
     assert max_rel(out["logits"].value, ref["logits"]) < T_
     assert max_rel(out["transformer_latent"].value, ref["transformer_latent"]) < (T_ if mode == "fp32" else 4e-2)
+    ref_err = {}
+    if mode == "bf16":      # the reference's own bf16 (autocast) error sets the scale, see the small-config test
+        sd2 = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            r2 = O.lvtr_forward(sd2, cfg, batch["x"], batch["mask"], batch["utterance"], batch["utt_mask"], rng)
+            l2 = O.total_loss(r2, kw)
+        l2.backward()
+        ref_err = {k: frob_rel(sd2[k].grad, sd[k].grad) for k, v in sd.items() if v.requires_grad}
     bad = []
     for name, p in model.named_parameters():
         e = frob_rel(p.grad, sd[name].grad)
-        if e > (3e-4 if mode == "fp32" else 6e-2):
-            bad.append((name, round(e, 5)))
+        lim = 3e-4 if mode == "fp32" else max(2e-2, 2.5 * ref_err[name])
+        if e > lim:
+            bad.append((name, round(e, 5), round(ref_err.get(name, 0.0), 5)))
     assert not bad, bad[:20]

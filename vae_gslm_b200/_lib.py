@@ -105,6 +105,7 @@ _SIGNATURES = {
     "vg_act_bwd": (C.c_int, [_p, _p, _p, _i64, C.c_int, C.c_int, _p]),
     "vg_attn_fwd": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p,
                               _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, C.c_int, _p]),
+    "vg_set_attn_backend": (C.c_int, [C.c_int]),
     "vg_attn_bwd_workspace": (_sz, [_i64, _i64, _i64, _i64, _i64]),
     "vg_attn_bwd": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _i64, _i64, _p, _p,
                               _i64, _i64, _i64, _i64, _i64, _i64, _f32, C.c_int, _p, _sz, _p]),
@@ -177,6 +178,11 @@ def call(name: str, *args) -> None:
     if rc != 0:
         raise RuntimeError(f"libvgslm {name} failed (rc={rc}): {last_error()}")
     launch_count += _KERNELS_PER_CALL.get(name, 1)
+
+
+def set_attention_backend(backend: str) -> None:
+    """'auto' (tcgen05 kernels for packed bf16, CUDA-core kernels otherwise), 'simt' or 'tcgen05'."""
+    call("vg_set_attn_backend", {"auto": 0, "simt": 1, "tcgen05": 2}[backend])
 
 
 def dtype_id(dt: torch.dtype) -> int:

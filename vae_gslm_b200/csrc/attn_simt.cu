@@ -394,7 +394,27 @@ static int attn_bwd_launch(const void* dout, const void* q, const void* k, const
 
 }  // namespace vg
 
+namespace vg {
+bool attn_tc_supported(int dtype, int64_t D, int64_t ld_q, int64_t ld_kv, const void* q, const void* k, const void* v,
+                       int64_t kv_batch_stride, int64_t kv_head_stride);
+int attn_tc_fwd_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out,
+                       int64_t ld_out, float* lse, const int32_t* kv_len, const float* slopes, int B, int H, int Tq,
+                       int Tk, int q_offset, float scale, cudaStream_t st);
+size_t attn_tc_bwd_workspace(int64_t B, int64_t H, int64_t Tq);
+int attn_tc_bwd_launch(const void* dout, int64_t ld_dout, const void* q, const void* k, const void* v, int64_t ld_q,
+                       int64_t ld_kv, const void* out, int64_t ld_out, const float* lse, void* dq, void* dk, void* dv,
+                       int64_t ld_dq, int64_t ld_dkv, const int32_t* kv_len, const float* slopes, int B, int H, int Tq,
+                       int Tk, int q_offset, float scale, void* workspace, cudaStream_t st);
+static int g_attn_backend = 0;     // 0 = auto (tcgen05 for bf16), 1 = CUDA-core parity kernels, 2 = tcgen05 required
+}  // namespace vg
+
 using namespace vg;
+
+extern "C" int vg_set_attn_backend(int backend) {
+  VG_REQUIRE(backend >= 0 && backend <= 2, -3, "vg_set_attn_backend: backend must be 0 (auto), 1 (simt) or 2 (tcgen05)");
+  g_attn_backend = backend;
+  return 0;
+}
 
 static int check_attn_shape(const char* fn, int64_t B, int64_t H, int64_t Tq, int64_t Tk, int64_t D,
                             int64_t q_offset, int dtype) {
@@ -415,12 +435,18 @@ extern "C" int vg_attn_fwd(const void* q, const void* k, const void* v, int64_t 
   AttnShape sh{(int)B, (int)H, (int)Tq, (int)Tk, (int)q_offset, ld_q, ld_kv, ld_out, scale,
                kv_batch_stride > 0 ? kv_batch_stride : Tk * ld_kv, kv_head_stride > 0 ? kv_head_stride : D};
   cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = attn_tc_supported(dtype, D, ld_q, ld_kv, q, k, v, kv_batch_stride, kv_head_stride) &&
+                     ld_out % 8 == 0 && aligned(out, 16);
+  VG_REQUIRE(g_attn_backend != 2 || tc_ok, -6, "vg_attn_fwd: tcgen05 backend needs packed bf16 q/k/v with ld %% 8 == 0");
+  if (tc_ok && g_attn_backend != 1)
+    return attn_tc_fwd_launch(q, k, v, ld_q, ld_kv, out, ld_out, lse, kv_len, slopes, (int)B, (int)H, (int)Tq, (int)Tk,
+                              (int)q_offset, scale, st);
   if (dtype == VG_F32) return attn_fwd_launch<float>(q, k, v, out, lse, kv_len, slopes, sh, st);
   return attn_fwd_launch<__nv_bfloat16>(q, k, v, out, lse, kv_len, slopes, sh, st);
 }
 
 extern "C" size_t vg_attn_bwd_workspace(int64_t B, int64_t H, int64_t Tq, int64_t, int64_t) {
-  return (size_t)(B * H * Tq) * sizeof(float);
+  return attn_tc_bwd_workspace(B, H, Tq);      // delta [B,H,Tq] (+ the tcgen05 path's fp32 dQ accumulator)
 }
 
 extern "C" int vg_attn_bwd(const void* dout, int64_t ld_dout, const void* q, const void* k, const void* v,
@@ -436,6 +462,13 @@ extern "C" int vg_attn_bwd(const void* dout, int64_t ld_dout, const void* q, con
   AttnBwdShape bs{{(int)B, (int)H, (int)Tq, (int)Tk, (int)q_offset, ld_q, ld_kv, ld_out, scale, Tk * ld_kv, D},
                   ld_dout, ld_dq, ld_dkv};
   cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = attn_tc_supported(dtype, D, ld_q, ld_kv, q, k, v, 0, 0) && ld_dout % 8 == 0 && ld_out % 8 == 0 &&
+                     ld_dq % 8 == 0 && ld_dkv % 8 == 0 && aligned(dout, 16) && aligned(out, 16) && aligned(dq, 16) &&
+                     aligned(dk, 16) && aligned(dv, 16);
+  VG_REQUIRE(g_attn_backend != 2 || tc_ok, -6, "vg_attn_bwd: tcgen05 backend needs packed bf16 tensors with ld %% 8 == 0");
+  if (tc_ok && g_attn_backend != 1)
+    return attn_tc_bwd_launch(dout, ld_dout, q, k, v, ld_q, ld_kv, out, ld_out, lse, dq, dk, dv, ld_dq, ld_dkv, kv_len,
+                              slopes, (int)B, (int)H, (int)Tq, (int)Tk, (int)q_offset, scale, workspace, st);
   if (dtype == VG_F32)
     return attn_bwd_launch<float>(dout, q, k, v, out, lse, dq, dk, dv, kv_len, slopes, bs, (float*)workspace, st);
   return attn_bwd_launch<__nv_bfloat16>(dout, q, k, v, out, lse, dq, dk, dv, kv_len, slopes, bs, (float*)workspace, st);

@@ -1,0 +1,557 @@
+// attn_tc.cu — causal ALiBi self-attention forward/backward on the 5th-generation tensor cores (bf16).
+// Reference: attention.py:52-78 (dense [B,H,T,T] additive mask + F.scaled_dot_product_attention) and
+// position/alibi.py.  Same contract as attn_simt.cu (which stays as the fp32 parity backend).
+//
+// Forward — one CTA per (batch, head, 128-query tile), two CTAs resident per SM:
+//   warp 0 lane 0 : TMA producer: Q once, then K (2-stage ring) and V tiles of 128 keys up to the causal limit
+//   warp 1        : TMEM allocator; lane 0 issues tcgen05.mma:  S = Q·Kᵀ (128x128x64)  and  O_j = P·V (128x64x128)
+//   warps 2..5    : softmax: thread = query row.  tcgen05.ld brings the row of S into registers, the bias
+//                   −slope_h·(i−j) and the (j ≤ i, j < kv_len) mask are applied in registers, online softmax
+//                   needs no shuffles, P goes to shared memory (bf16, 128B-swizzled, as the K-major A operand
+//                   of the second MMA) and the per-tile O_j is folded into a register accumulator.
+// Backward — one CTA per (batch, head, 128-key tile), looping over the query tiles that can see it:
+//   S = Q·Kᵀ and dP = dO·Vᵀ land in TMEM; threads form P = exp2(S' − LSE) and dS = P∘(dP − δ)·scale in
+//   registers and store both (bf16, swizzled) once; the SAME shared-memory bytes then serve as MN-major A
+//   operand for dV += Pᵀ·dO and dK += dSᵀ·Q and as K-major A operand for dQ_i = dS·K (only the descriptor's
+//   major bit differs).  dK/dV accumulate in TMEM across the loop; dQ_i is reduced into an fp32 buffer with
+//   vector red.global.add (as FlashAttention-2 does) and converted to bf16 by a tail kernel.
+#include <math_constants.h>
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace vg {
+using namespace sm100;
+
+int make_tmap_bf16_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1,
+                      int64_t stride2, int box0, int box1);
+
+constexpr int TQ = 128;            // query rows per tile (UMMA M)
+constexpr int TK = 128;            // keys per tile
+constexpr int HD = 64;             // head dim
+constexpr int TILE_BYTES = 128 * HD * 2;      // 16 KB: a [128 x 64] bf16 tile, rows of 128 B, SWIZZLE_128B
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct AttnTcShape {
+  int B, H, Tq, Tk, q_offset;
+  float scale;
+};
+
+// byte offset of the 16-byte piece `piece` (0..15: 8 bf16 each) of row `row` inside a [128 x 128] bf16 tile stored
+// as two [128 x 64] SWIZZLE_128B halves (what TMA would produce and what the UMMA descriptors expect)
+__device__ __forceinline__ uint32_t sw128_piece(int row, int piece) {
+  return (uint32_t)((piece >> 3) * TILE_BYTES + row * 128 + (((piece & 7) ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// K-major A/B operand: tile rows at 128 B pitch; k-step of 16 elements = +32 B inside the 64-wide half
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kstep) {
+  return make_smem_desc_sw128(tile_addr + (uint32_t)((kstep >> 2) * TILE_BYTES + (kstep & 3) * 32), 16, 1024);
+}
+// MN-major operand: tile stored [k rows x 64 mn] (+ further 64-wide mn halves every TILE_BYTES); k-step = 16 rows
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kstep) {
+  return make_smem_desc_sw128(tile_addr + (uint32_t)(kstep * 2048), TILE_BYTES, 1024);
+}
+
+// =========================================================================================== forward
+constexpr int FWD_THREADS = 192;
+constexpr int FWD_SMEM = 5 * TILE_BYTES /*Q, K0, K1, V*/ + TILE_BYTES /*P second half*/ + 1024 + 256;
+// layout: Q | K0 | K1 | V | P(2 halves)
+
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int64_t ld_out,
+                   float* __restrict__ lse, const int32_t* __restrict__ kv_len, const float* __restrict__ slopes,
+                   AttnTcShape sh) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;            // 2 stages
+  uint8_t* sV = smem + 3 * TILE_BYTES;
+  uint8_t* sP = smem + 4 * TILE_BYTES;        // 2 halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 6,
+           *s_full = bars + 7, *p_full = bars + 8, *o_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // heavy (late) query tiles first: causal work grows with the tile index
+  const int n_qt = (sh.Tq + TQ - 1) / TQ;
+  const int qt = n_qt - 1 - (int)blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * TQ;
+  const int klen = kv_len ? min(kv_len[b], sh.Tk) : sh.Tk;
+  const int q_abs_last = sh.q_offset + min(q0 + TQ, sh.Tq) - 1;
+  const int k_end = min(klen, q_abs_last + 1);
+  const int n_kt = (k_end + TK - 1) / TK;       // may be 0 (empty sequence)
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(&k_full[0], 1); mbar_init(&k_full[1], 1);
+    mbar_init(&k_empty[0], 1); mbar_init(&k_empty[1], 1);
+    mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;            // columns [0,128): S
+  const uint32_t tO = tmem_base + 128;      // columns [128,192): per-tile O_j
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    if (n_kt > 0) {
+      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, h * HD, q0, b);
+    }
+    for (int j = 0; j < n_kt; ++j) {
+      const int s = j & 1;
+      mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
+      mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+      tma_load_3d(sK + s * TILE_BYTES, &tmK, &k_full[s], h * HD, j * TK, b);
+      mbar_wait(v_empty, (j & 1) ^ 1);
+      mbar_arrive_expect_tx(v_full, TILE_BYTES);
+      tma_load_3d(sV, &tmV, v_full, h * HD, j * TK, b);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);     // S = Q·Kᵀ : both K-major
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);      // O = P·V  : A K-major, B (V) MN-major
+    const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aV = smem_u32(sV);
+    if (n_kt > 0) { mbar_wait(q_full, 0); }
+    for (int j = 0; j < n_kt; ++j) {
+      const int s = j & 1;
+      mbar_wait(&k_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t aK = smem_u32(sK + s * TILE_BYTES);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tS, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_s, k != 0);
+      umma_commit(&k_empty[s]);
+      umma_commit(s_full);
+      mbar_wait(p_full, j & 1);                 // P_j written (and S_j fully consumed)
+      mbar_wait(v_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < TK / 16; ++k) umma_f16_ss(tO, desc_kmajor(aP, k), desc_mnmajor(aV, k), idesc_o, k != 0);
+      umma_commit(v_empty);
+      umma_commit(o_full);
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax (thread = query row) =====================
+    const int rb = (warp & 3) * 32;             // TMEM lane quadrant accessible to this warp
+    const int r = rb + lane;                    // row inside the tile
+    const int iq = q0 + r;
+    const int ia = sh.q_offset + iq;
+    const float slope2 = (slopes ? slopes[h] : 0.f) * kLog2e;
+    const float scale2 = sh.scale * kLog2e;
+    const uint32_t lane_addr = (uint32_t)rb << 16;
+    float m = -CUDART_INF_F, l = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+
+    for (int j = 0; j < n_kt; ++j) {
+      const int j0 = j * TK;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row maximum of the biased, masked scores (log2 domain)
+      float mx = -CUDART_INF_F;
+#pragma unroll 1
+      for (int c = 0; c < TK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tS + lane_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int ja = j0 + c * 32 + e;
+          const float s2 = __uint_as_float(v[e]) * scale2 - slope2 * (float)(ia - ja);
+          mx = fmaxf(mx, (ja <= ia && ja < klen) ? s2 : -CUDART_INF_F);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
+      const float corr = ex2_approx(m - m_use);            // m = -inf → 0
+      float rsum = 0.f;
+      // pass 2: P = exp2(s − m), written bf16 + swizzled as the A operand of the P·V MMA
+#pragma unroll 1
+      for (int c = 0; c < TK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tS + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int ja = j0 + c * 32 + e;
+          const float s2 = __uint_as_float(v[e]) * scale2 - slope2 * (float)(ia - ja);
+          p[e] = (ja <= ia && ja < klen) ? ex2_approx(s2 - m_use) : 0.f;
+          rsum += p[e];
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
+          pk.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+          pk.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
+          pk.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(sP + sw128_piece(r, c * 4 + g)) = pk;
+        }
+      }
+      l = l * corr + rsum;
+      m = m_new;
+      tc_fence_before();            // our tcgen05.ld of S_j are ordered before the MMA that overwrites S
+      fence_proxy_async();          // generic-proxy writes of P visible to the tensor core (async proxy)
+      mbar_arrive(p_full);
+      // fold O_j into the register accumulator
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tO + lane_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[c * 32 + e] = o[c * 32 + e] * corr + __uint_as_float(v[e]);
+      }
+      tc_fence_before();
+    }
+    if (iq < sh.Tq) {
+      const bool valid = ia < klen && l > 0.f;
+      const float inv = valid ? 1.f / l : 0.f;
+      __nv_bfloat16* op = out + ((int64_t)b * sh.Tq + iq) * ld_out + h * HD;
+#pragma unroll
+      for (int g = 0; g < HD / 8; ++g) {
+        uint4 pk;
+        pk.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv);
+        pk.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
+        pk.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv);
+        pk.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(op + g * 8) = pk;
+      }
+      lse[((int64_t)b * sh.H + h) * sh.Tq + iq] = valid ? (m + log2f(l)) * kLn2 : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// =========================================================================================== backward
+constexpr int BWD_THREADS = 192;
+// layout: K | V | Q0 | Q1 | dO0 | dO1 | P (2 halves) | dS (2 halves) = 10 tiles
+constexpr int BWD_SMEM = 10 * TILE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
+                   __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int64_t ld_dkv,
+                   const int32_t* __restrict__ kv_len, const float* __restrict__ slopes, AttnTcShape sh) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + TILE_BYTES;
+  uint8_t* sQ = smem + 2 * TILE_BYTES;        // 2 stages
+  uint8_t* sdO = smem + 4 * TILE_BYTES;       // 2 stages
+  uint8_t* sP = smem + 6 * TILE_BYTES;        // 2 halves
+  uint8_t* sdS = smem + 8 * TILE_BYTES;       // 2 halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE_BYTES);
+  uint64_t *kv_full = bars, *qdo_full = bars + 1, *qdo_empty = bars + 3, *sdp_full = bars + 5, *pds_full = bars + 6,
+           *dq_full = bars + 7, *acc_full = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int j0 = kt * TK;
+  const int klen = kv_len ? min(kv_len[b], sh.Tk) : sh.Tk;
+  // query tiles that can see key j0: q_offset + iq >= j0; rows at/after klen are padded queries (P = 0)
+  int i_first = (j0 - sh.q_offset) / TQ;
+  if (j0 - sh.q_offset < 0) i_first = 0;
+  const int q_valid_end = min(sh.Tq, klen - sh.q_offset);            // queries with ia < klen
+  const int n_qt_total = (max(q_valid_end, 0) + TQ - 1) / TQ;
+  const int n_it = (j0 < klen) ? max(n_qt_total - i_first, 0) : 0;   // iterations of the query-tile loop
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
+    mbar_init(kv_full, 1);
+    mbar_init(&qdo_full[0], 1); mbar_init(&qdo_full[1], 1);
+    mbar_init(&qdo_empty[0], 1); mbar_init(&qdo_empty[1], 1);
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 128); mbar_init(dq_full, 1); mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
+                 tdQ = tmem_base + 384;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    if (n_it > 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
+      tma_load_3d(sK, &tmK, kv_full, h * HD, j0, b);
+      tma_load_3d(sV, &tmV, kv_full, h * HD, j0, b);
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      const int q0 = (i_first + it) * TQ;
+      mbar_wait(&qdo_empty[s], ((it >> 1) & 1) ^ 1);
+      mbar_arrive_expect_tx(&qdo_full[s], 2 * TILE_BYTES);
+      tma_load_3d(sQ + s * TILE_BYTES, &tmQ, &qdo_full[s], h * HD, q0, b);
+      tma_load_3d(sdO + s * TILE_BYTES, &tmdO, &qdo_full[s], h * HD, q0, b);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_sp = make_idesc_bf16(128, 128, 0, 0);    // S = Q·Kᵀ, dP = dO·Vᵀ
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);      // dV = Pᵀ·dO, dK = dSᵀ·Q (A, B MN-major)
+    constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);      // dQ = dS·K       (A K-major, B MN-major)
+    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
+    if (n_it > 0) mbar_wait(kv_full, 0);
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      const uint32_t aQ = smem_u32(sQ + s * TILE_BYTES), adO = smem_u32(sdO + s * TILE_BYTES);
+      mbar_wait(&qdo_full[s], (it >> 1) & 1);      // (S/dP of the previous tile were consumed before pds_full(it-1))
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tS, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_sp, k != 0);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tdP, desc_kmajor(adO, k), desc_kmajor(aV, k), idesc_sp, k != 0);
+      umma_commit(sdp_full);
+      mbar_wait(pds_full, it & 1);                 // P and dS in shared memory; dQ_{it-1} has been drained from TMEM
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < TQ / 16; ++k)
+        umma_f16_ss(tdV, desc_mnmajor(aP, k), desc_mnmajor(adO, k), idesc_t, (it | k) != 0);
+#pragma unroll
+      for (int k = 0; k < TQ / 16; ++k)
+        umma_f16_ss(tdK, desc_mnmajor(adS, k), desc_mnmajor(aQ, k), idesc_t, (it | k) != 0);
+#pragma unroll
+      for (int k = 0; k < TK / 16; ++k) umma_f16_ss(tdQ, desc_kmajor(adS, k), desc_mnmajor(aK, k), idesc_q, k != 0);
+      umma_commit(&qdo_empty[s]);
+      umma_commit(dq_full);
+    }
+    if (n_it > 0) umma_commit(acc_full);
+  } else if (warp >= 2) {
+    // ===================== softmax-backward threads (thread = query row of the current tile) =====================
+    const int rb = (warp & 3) * 32;
+    const int r = rb + lane;
+    const uint32_t lane_addr = (uint32_t)rb << 16;
+    const float slope2 = (slopes ? slopes[h] : 0.f) * kLog2e;
+    const float scale2 = sh.scale * kLog2e;
+    const float* lse_row = lse + ((int64_t)b * sh.H + h) * sh.Tq;
+    const float* delta_row = delta + ((int64_t)b * sh.H + h) * sh.Tq;
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_first + it) * TQ;
+      const int iq = q0 + r;
+      const int ia = sh.q_offset + iq;
+      const bool row_ok = iq < sh.Tq && ia < klen;
+      const float L2 = row_ok ? lse_row[iq] * kLog2e : 0.f;
+      const float dl = row_ok ? delta_row[iq] : 0.f;
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < TK / 16; ++c) {
+        uint32_t vs[16], vp[16];
+        tmem_ld_32x32b_x16(tS + lane_addr + c * 16, vs);
+        tmem_ld_32x32b_x16(tdP + lane_addr + c * 16, vp);
+        tmem_ld_wait();
+        float p[16], ds[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int ja = j0 + c * 16 + e;
+          const bool ok = row_ok && ja <= ia && ja < klen;
+          const float s2 = __uint_as_float(vs[e]) * scale2 - slope2 * (float)(ia - ja);
+          p[e] = ok ? ex2_approx(s2 - L2) : 0.f;
+          ds[e] = p[e] * (__uint_as_float(vp[e]) - dl) * sh.scale;
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 pk, dk4;
+          pk.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);  pk.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+          pk.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);  pk.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+          dk4.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]); dk4.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
+          dk4.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]); dk4.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
+          const uint32_t off = sw128_piece(r, c * 2 + g);
+          *reinterpret_cast<uint4*>(sP + off) = pk;
+          *reinterpret_cast<uint4*>(sdS + off) = dk4;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(pds_full);
+      // dQ_i partial of this key tile → fp32 accumulator in global memory
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      float* dq_row = dq_acc + ((int64_t)b * sh.Tq + iq) * ((int64_t)sh.H * HD) + h * HD;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tdQ + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
+                                   __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
+            atomicAdd(reinterpret_cast<float4*>(dq_row + c * 32 + g * 4), f);
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    // ---- dK / dV of this key tile (thread = key row)
+    const int jr = j0 + r;
+    if (n_it > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* dst = (which == 0 ? dv : dk) + ((int64_t)b * sh.Tk + jr) * ld_dkv + h * HD;
+      const uint32_t tsrc = (which == 0 ? tdV : tdK) + lane_addr;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        if (n_it > 0) {
+          tmem_ld_32x32b_x32(tsrc + c * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0u;
+        }
+        if (jr < sh.Tk) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+            pk.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+            pk.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+            pk.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// delta[b,h,i] = Σ_d dO[i,d]·O[i,d]   (bf16 inputs)
+__global__ void attn_tc_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld_dout,
+                                     const __nv_bfloat16* __restrict__ out, int64_t ld_out, float* __restrict__ delta,
+                                     int B, int H, int Tq) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;      // 8 lanes per (b,h,i) row
+  const int sub = threadIdx.x & 7;
+  if (w >= (int64_t)B * H * Tq) return;     // whole 8-lane groups exit together; shuffles below stay in-group
+  const int i = (int)(w % Tq);
+  const int h = (int)((w / Tq) % H);
+  const int b = (int)(w / ((int64_t)Tq * H));
+  Vec8<__nv_bfloat16> a, o;
+  a.load(dout + ((int64_t)b * Tq + i) * ld_dout + h * HD + sub * 8);
+  o.load(out + ((int64_t)b * Tq + i) * ld_out + h * HD + sub * 8);
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s = fmaf(a.v[e], o.v[e], s);
+  const unsigned grp_mask = 0xffu << ((threadIdx.x & 31) & ~7);
+  s += __shfl_xor_sync(grp_mask, s, 4);
+  s += __shfl_xor_sync(grp_mask, s, 2);
+  s += __shfl_xor_sync(grp_mask, s, 1);
+  if (sub == 0) delta[w] = s;
+}
+
+__global__ void attn_tc_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t ld_dq,
+                                          int64_t rows, int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // over rows * C/8
+  const int c8 = C / 8;
+  if (i >= rows * c8) return;
+  const int64_t row = i / c8;
+  const int c = (int)(i % c8) * 8;
+  Vec8<float> a;
+  a.load(acc + row * C + c);
+  Vec8<__nv_bfloat16> o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = a.v[e];
+  o.store(dq + row * ld_dq + c);
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+bool attn_tc_supported(int dtype, int64_t D, int64_t ld_q, int64_t ld_kv, const void* q, const void* k, const void* v,
+                       int64_t kv_batch_stride, int64_t kv_head_stride) {
+  return dtype == VG_BF16 && D == HD && ld_q % 8 == 0 && ld_kv % 8 == 0 && aligned(q, 16) && aligned(k, 16) &&
+         aligned(v, 16) && kv_batch_stride == 0 && kv_head_stride == 0;
+}
+
+int attn_tc_fwd_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out,
+                       int64_t ld_out, float* lse, const int32_t* kv_len, const float* slopes, int B, int H, int Tq,
+                       int Tk, int q_offset, float scale, cudaStream_t st) {
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tmQ, q, (int64_t)H * HD, Tq, B, ld_q, (int64_t)Tq * ld_q, HD, TQ))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmK, k, (int64_t)H * HD, Tk, B, ld_kv, (int64_t)Tk * ld_kv, HD, TK))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmV, v, (int64_t)H * HD, Tk, B, ld_kv, (int64_t)Tk * ld_kv, HD, TK))) return rc;
+  static bool set = false;
+  if (!set) {
+    VG_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    set = true;
+  }
+  AttnTcShape sh{B, H, Tq, Tk, q_offset, scale};
+  dim3 grid((unsigned)((Tq + TQ - 1) / TQ), (unsigned)H, (unsigned)B);
+  attn_tc_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, (__nv_bfloat16*)out, ld_out, lse, kv_len,
+                                                          slopes, sh);
+  VG_LAUNCH_CHECK("vg_attn_fwd(tcgen05)");
+  return 0;
+}
+
+size_t attn_tc_bwd_workspace(int64_t B, int64_t H, int64_t Tq) {
+  return align_up((size_t)(B * H * Tq) * sizeof(float), 256) + (size_t)(B * Tq * H * HD) * sizeof(float);
+}
+
+int attn_tc_bwd_launch(const void* dout, int64_t ld_dout, const void* q, const void* k, const void* v, int64_t ld_q,
+                       int64_t ld_kv, const void* out, int64_t ld_out, const float* lse, void* dq, void* dk, void* dv,
+                       int64_t ld_dq, int64_t ld_dkv, const int32_t* kv_len, const float* slopes, int B, int H, int Tq,
+                       int Tk, int q_offset, float scale, void* workspace, cudaStream_t st) {
+  float* delta = (float*)workspace;
+  float* dq_acc = (float*)((uint8_t*)workspace + align_up((size_t)B * H * Tq * sizeof(float), 256));
+  const int64_t nrows = (int64_t)B * H * Tq;
+  attn_tc_delta_kernel<<<(unsigned)ceil_div(nrows * 8, 256), 256, 0, st>>>((const __nv_bfloat16*)dout, ld_dout,
+                                                                          (const __nv_bfloat16*)out, ld_out, delta, B,
+                                                                          H, Tq);
+  VG_LAUNCH_CHECK("vg_attn_bwd(tcgen05 delta)");
+  VG_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * Tq * H * HD * sizeof(float), st));
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tmQ, q, (int64_t)H * HD, Tq, B, ld_q, (int64_t)Tq * ld_q, HD, TQ))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmK, k, (int64_t)H * HD, Tk, B, ld_kv, (int64_t)Tk * ld_kv, HD, TK))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmV, v, (int64_t)H * HD, Tk, B, ld_kv, (int64_t)Tk * ld_kv, HD, TK))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmdO, dout, (int64_t)H * HD, Tq, B, ld_dout, (int64_t)Tq * ld_dout, HD, TQ))) return rc;
+  static bool set = false;
+  if (!set) {
+    VG_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    set = true;
+  }
+  AttnTcShape sh{B, H, Tq, Tk, q_offset, scale};
+  dim3 grid((unsigned)((Tk + TK - 1) / TK), (unsigned)H, (unsigned)B);
+  attn_tc_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, lse, delta, dq_acc,
+                                                          (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, ld_dkv, kv_len,
+                                                          slopes, sh);
+  VG_LAUNCH_CHECK("vg_attn_bwd(tcgen05)");
+  const int C = H * HD;
+  const int64_t n = (int64_t)B * Tq * (C / 8);
+  attn_tc_dq_convert_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dq, ld_dq,
+                                                                       (int64_t)B * Tq, C);
+  VG_LAUNCH_CHECK("vg_attn_bwd(tcgen05 dq convert)");
+  return 0;
+}
+
+}  // namespace vg
