@@ -316,3 +316,30 @@ def test_full_config_against_oracle(mode):
         if e > lim:
             bad.append((name, round(e, 5), round(ref_err.get(name, 0.0), 5)))
     assert not bad, bad[:20]
+
+
+def test_cuda_graph_decode_matches_eager(golden):
+    """the graphed single-token step (device-resident cache position) reproduces the eager loop bit for bit
+    under greedy decoding with the prior noise switched off (temperature 0)."""
+    from vae_gslm_b200.trainers.speech.sampler import GraphedStep
+    d = golden["decode"]
+    runs = []
+    for use_graph in (False, True):
+        model = build_small(golden).eval()
+        model.transformer[0].cache_len_hint = 64
+        o = model.step(d["prompt"].to(DEV), past_kv=None, temperature=0.0, push_init_state=True, greedy=True,
+                       init_state=d["init_state"].to(DEV))
+        state, kv = o["output"][:, -1:], o["kv"]
+        frames = []
+        graphed = None
+        for i in range(12):
+            if use_graph and i >= 2:
+                graphed = graphed or GraphedStep(model, state, kv, temperature=0.0, greedy=True)
+                state = graphed().clone()
+            else:
+                o = model.step(state, past_kv=kv, temperature=0.0, greedy=True)
+                state, kv = o["output"], o["kv"]
+            frames.append(state)
+        runs.append(torch.cat(frames, 1).cpu())
+        assert kv[0].cache.length == d["prompt"].shape[1] + 1 + 12
+    assert torch.equal(runs[0], runs[1])

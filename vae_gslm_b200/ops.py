@@ -52,15 +52,18 @@ def lowp(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     shadow = getattr(weight, "_vg_shadow", None)
     if shadow is not None and shadow.dtype == dtype:
         return shadow
-    key = (weight.data_ptr(), tuple(weight.shape), dtype)
-    ent = _shadow_cache.get(key)
+    # memoised ON the weight tensor (dies with it — an address-keyed cache could alias a freed tensor's entry)
+    ent = getattr(weight, "_vg_lowp", None)
     ver = weight._version
-    if ent is not None and ent[0] == ver and ent[1].device == weight.device:
+    if ent is not None and ent[0] == ver and ent[1].dtype == dtype and ent[1].device == weight.device:
         return ent[1]
     src = weight.detach().contiguous()
     out = torch.empty(src.shape, dtype=dtype, device=src.device)
     L.call("vg_cast_f32_to_bf16", L.ptr(src), L.ptr(out), src.numel(), L.stream())
-    _shadow_cache[key] = (ver, out)
+    try:
+        weight._vg_lowp = (ver, out)
+    except Exception:
+        pass
     return out
 
 
@@ -408,8 +411,10 @@ def attention_decode(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Te
     B, C3 = qkv.shape
     _, H, Tmax, D = k_cache.shape
     scale = scale if scale is not None else 1.0 / math.sqrt(D)
-    if splits is None:      # fill ~2 waves of 148 SMs when the batch alone cannot
-        splits = max(1, min(16, (2 * 148 + B * H - 1) // (B * H), (pos + 64) // 64))
+    if splits is None:      # fill ~2 waves of 148 SMs when the batch alone cannot; with a device-resident position
+        # (CUDA-graph replay) the split count is frozen at capture time, so size it for the whole cache
+        horizon = Tmax if pos_dev is not None else pos + 1
+        splits = max(1, min(16, (2 * 148 + B * H - 1) // (B * H), (horizon + 63) // 64))
     out = torch.empty((B, C3 // 3), dtype=qkv.dtype, device=qkv.device)
     ws = L.workspace(L.load().vg_attn_decode_workspace(B, H, D, splits), qkv.device)
     L.call("vg_attn_decode", L.ptr(qkv), L.ptr(k_cache), L.ptr(v_cache), L.ptr(out), L.ptr(slopes), B, H, D, Tmax,
