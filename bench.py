@@ -142,19 +142,19 @@ def run_ours(args):
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
+    from vae_gslm_b200.trainers.speech.lvtr import TrainStep
+    train_step = TrainStep(model, arena, reducer, resident, lr=lr, kld_weight=KW,
+                           use_cuda_graph=not args.no_cuda_graph)
+    if rank == 0 and train_step.graph is None and not args.no_cuda_graph:
+        print("cuda-graph capture failed, running eager:", getattr(train_step, "capture_error", "?"), file=sys.stderr)
+
     def step(batch, from_host):
         if from_host:
-            batch = {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
-        arena.zero_grad()
-        reducer.prepare(last_micro_batch=True)
-        out = model(TensorMask(batch["x"], batch["mask"]), utterance=TensorMask(batch["utterance"], batch["utt_mask"]))
-        terms = assemble_loss(out, kld_weight=KW)
-        terms["loss"].backward()
-        reducer.finish()
-        arena.adamw_step(lr)
+            train_step.load(batch)                          # pinned host → static device buffers (H2D every step)
+        loss = train_step()
         if from_host:
-            return float(terms["loss"].item())              # device→host read of the step's result
-        return terms["loss"]
+            return float(loss.item())                       # device→host read of the step's result
+        return loss
 
     def timed(nsteps, from_host):
         if world > 1:
@@ -177,9 +177,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = _lib.launch_count
     ms, last_loss = timed(args.steps, False)
-    launches = _lib.launch_count - launches0
+    launches = train_step.launches_per_step * args.steps     # libvgslm kernels (graph replays re-launch all of them)
     clocks = sampler.stop()
     ms_e2e, loss_host = timed(args.steps, True)
 
@@ -189,7 +188,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (gemm_tc_kernel): one extra, instrumented step (not part of the timing)
     ops.PROFILE = []
-    step(resident, False)
+    train_step._body(device_hyper=False)                     # eager on purpose: CUDA events around every GEMM launch
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in prof)
@@ -218,7 +217,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": loss_host},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-        "loss": float(last_loss),
+        "loss": float(last_loss), "step_mode": train_step.mode,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline_sample(model, hp)
@@ -358,6 +357,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="frames per sequence (20 s segments at 50 Hz)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="run the training step eagerly (launch-bound)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -342,4 +342,6 @@ def test_cuda_graph_decode_matches_eager(golden):
             frames.append(state)
         runs.append(torch.cat(frames, 1).cpu())
         assert kv[0].cache.length == d["prompt"].shape[1] + 1 + 12
-    assert torch.equal(runs[0], runs[1])
+    # identical tokens; latents equal up to the split-KV summation order (the graph freezes the split count)
+    assert torch.equal(runs[0][..., 0], runs[1][..., 0])
+    assert max_rel(runs[1][..., 1:], runs[0][..., 1:]) < 1e-5

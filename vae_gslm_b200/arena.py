@@ -132,18 +132,26 @@ class ParamArena:
     def adamw_step(self, lr: float, beta1: float = 0.9, beta2: float = 0.98, eps: float = 1e-8,
                    grad_scale: float = 1.0, use_device_hyper: bool = False) -> None:
         """torch.optim.AdamW semantics over both arenas; refreshes the bf16 shadows in the same pass."""
-        self.step_count += 1
-        bc1 = 1.0 - beta1 ** self.step_count
-        bc2 = 1.0 - beta2 ** self.step_count
+        bc1, bc2 = self.stage_hyper(lr, beta1, beta2)
         for grp, hyper, host in zip(self.groups, self.hyper, self._hyper_host):
             hp = None
             if use_device_hyper:
-                host[0], host[1], host[2], host[3] = lr, 1.0 / bc1, bc2 ** -0.5, 1.0 - lr * grp.weight_decay
+                # the copy node reads the pinned host buffer at EXECUTION time, so a captured graph picks up
+                # whatever stage_hyper() wrote before each replay
                 hyper.copy_(host, non_blocking=True)
                 hp = L.ptr(hyper)
             L.call("vg_adamw_step", L.ptr(grp.p), L.ptr(grp.g), L.ptr(grp.m), L.ptr(grp.v),
                    L.ptr(grp.shadow) if grp.shadow is not None else None, grp.numel, lr, beta1, beta2, eps,
                    grp.weight_decay, bc1, bc2, grad_scale, hp, L.stream())
+
+    def stage_hyper(self, lr: float, beta1: float = 0.9, beta2: float = 0.98):
+        """advance the step counter and write {lr, 1/bc1, 1/sqrt(bc2), 1-lr*wd} to the pinned staging buffers."""
+        self.step_count += 1
+        bc1 = 1.0 - beta1 ** self.step_count
+        bc2 = 1.0 - beta2 ** self.step_count
+        for grp, host in zip(self.groups, self._hyper_host):
+            host[0], host[1], host[2], host[3] = lr, 1.0 / bc1, bc2 ** -0.5, 1.0 - lr * grp.weight_decay
+        return bc1, bc2
 
     # ------------------------------------------------------------------ data-parallel buckets
     def buckets(self, bucket_bytes: int = 64 << 20) -> List[Tuple[torch.Tensor, List[nn.Parameter]]]:

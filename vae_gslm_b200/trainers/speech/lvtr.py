@@ -1,10 +1,10 @@
-"""Loss assembly of the VAE-GSLM training step (reference ``trainers/speech/lvtr.py:103-145``) and a
-minimal single-process training step around it.  The Lightning shell of the reference is out of scope
+"""Loss assembly of the VAE-GSLM training step (reference ``trainers/speech/lvtr.py:103-145``) and the
+single-process training step around it (``TrainStep``).  The Lightning shell of the reference is out of scope
 (SURVEY §2 row 15); data-parallel plumbing lives in ``vae_gslm_b200.dp``.
 """
 from __future__ import annotations
 
-from typing import Mapping, Optional
+from typing import Dict, Mapping, Optional
 
 import torch
 
@@ -23,9 +23,10 @@ def kld_weight_at(global_step: int, kld_scale: float, warmup_kld: int = 0, zero_
     return w
 
 
-def assemble_loss(output: Mapping, kld_weight: float, rec_loss_scale: float = 1.0, entropy_weight: float = 1.0,
+def assemble_loss(output: Mapping, kld_weight, rec_loss_scale: float = 1.0, entropy_weight: float = 1.0,
                   token_kld_weight: float = 0.5, use_fused_kl: bool = True) -> Mapping[str, torch.Tensor]:
-    """loss = rec·scale + kld·kw + ce·token_kld_weight·kw — every term a SUM over valid frames (:122-130)."""
+    """loss = rec·scale + kld·kw + ce·token_kld_weight·kw — every term a SUM over valid frames (:122-130).
+    ``kld_weight`` may be a python float or a 0-dim device tensor (CUDA-graph replay)."""
     if use_fused_kl and entropy_weight == 1.0 and "kl_sum" in output:
         kld = output["kl_sum"]                       # computed inside the latent_back kernel
     else:
@@ -42,3 +43,79 @@ def assemble_loss(output: Mapping, kld_weight: float, rec_loss_scale: float = 1.
 def make_model_input(tokens: TensorMask, mel: TensorMask) -> TensorMask:
     """channel-interleaved model input [B,T,1+n_mels]: token id as float ⊕ mel (:117-118)."""
     return TensorMask(tokens.value.to(mel.value.dtype), tokens.mask).expand().cat(mel)
+
+
+class TrainStep:
+    """zero-grad → forward → loss → backward → gradient all-reduce → fused AdamW, on static input buffers.
+
+    With ``use_cuda_graph`` the whole sequence (≈5,000 kernel launches: ours, cuDNN/cuBLAS for the conv stack,
+    NCCL) is captured ONCE and replayed, which removes the Python/launch overhead that otherwise bounds the step.
+    Per-step scalars that change (learning rate, Adam bias corrections, KL weight) live in device memory and are
+    refreshed from pinned host memory by copy nodes inside the graph.
+    """
+
+    def __init__(self, model, arena, reducer, example_batch: Dict[str, torch.Tensor], *, lr: float,
+                 kld_weight: float = 0.04, betas=(0.9, 0.98), eps: float = 1e-8, use_cuda_graph: bool = True,
+                 warmup_iters: int = 3) -> None:
+        self.model, self.arena, self.reducer = model, arena, reducer
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.static = {k: v.clone() for k, v in example_batch.items()}        # device-resident input buffers
+        dev = next(iter(self.static.values())).device
+        self.kw_dev = torch.full((), float(kld_weight), device=dev)
+        self.loss = torch.zeros((), device=dev)
+        self.terms = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.mode = "eager"
+        from ... import _lib
+        n0 = _lib.launch_count
+        self._body(device_hyper=False)                      # also the first warm-up iteration
+        self.launches_per_step = _lib.launch_count - n0     # libvgslm kernels per step (bench.py's gpu_launches)
+        if use_cuda_graph:
+            try:
+                self._capture(warmup_iters)
+                self.mode = "cuda-graph"
+            except Exception as e:      # keep the eager path usable; bench.py reports which mode ran
+                self.graph = None
+                self.capture_error = repr(e)
+                torch.cuda.synchronize()
+
+    # the work of one step, on whatever stream is current
+    def _body(self, device_hyper: bool) -> None:
+        s = self.static
+        self.arena.zero_grad()
+        self.reducer.prepare(last_micro_batch=True)
+        out = self.model(TensorMask(s["x"], s["mask"]), utterance=TensorMask(s["utterance"], s["utt_mask"]))
+        terms = assemble_loss(out, kld_weight=self.kw_dev)
+        terms["loss"].backward()
+        self.reducer.finish()
+        self.arena.adamw_step(self.lr, self.betas[0], self.betas[1], self.eps, use_device_hyper=device_hyper)
+        self.loss.copy_(terms["loss"].detach())
+
+    def _capture(self, warmup_iters: int) -> None:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up off the default stream, as torch requires
+            for _ in range(warmup_iters):
+                self._body(device_hyper=True)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        steps_before = self.arena.step_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body(device_hyper=True)
+        self.arena.step_count = steps_before               # capture advanced the host counter without running
+
+    def load(self, batch: Dict[str, torch.Tensor]) -> None:
+        """copy a (pinned host or device) batch into the static input buffers."""
+        for k, v in batch.items():
+            self.static[k].copy_(v, non_blocking=True)
+
+    def __call__(self, lr: Optional[float] = None) -> torch.Tensor:
+        if lr is not None:
+            self.lr = lr
+        if self.graph is not None:
+            self.arena.stage_hyper(self.lr, self.betas[0], self.betas[1])     # pinned values read by the graph
+            self.graph.replay()
+        else:
+            self._body(device_hyper=False)
+        return self.loss
