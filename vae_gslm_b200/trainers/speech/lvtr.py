@@ -66,18 +66,29 @@ class TrainStep:
         self.terms = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.mode = "eager"
+        self.capture_error: Optional[str] = None
+        # Every execution of the step body — warm-up, capture, eager — runs on ONE private stream.  autograd's
+        # AccumulateGrad nodes remember the stream they were first used on (our parameters keep them alive through
+        # the pre-assigned arena .grad views and the reducer hooks); if that were the default stream, capture on
+        # another stream would be invalidated.
+        self.stream = torch.cuda.Stream(device=dev)
         from ... import _lib
         n0 = _lib.launch_count
-        self._body(device_hyper=False)                      # also the first warm-up iteration
+        self._run_eager(device_hyper=False)                 # also the first warm-up iteration
         self.launches_per_step = _lib.launch_count - n0     # libvgslm kernels per step (bench.py's gpu_launches)
         if use_cuda_graph:
             try:
                 self._capture(warmup_iters)
                 self.mode = "cuda-graph"
-            except Exception as e:      # keep the eager path usable; bench.py reports which mode ran
+            except Exception as e:      # NB: a failed capture leaves torch's RNG in capture mode; callers restart
                 self.graph = None
                 self.capture_error = repr(e)
-                torch.cuda.synchronize()
+
+    def _run_eager(self, device_hyper: bool) -> None:
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self._body(device_hyper)
+        torch.cuda.current_stream().wait_stream(self.stream)
 
     # the work of one step, on whatever stream is current
     def _body(self, device_hyper: bool) -> None:
@@ -92,16 +103,12 @@ class TrainStep:
         self.loss.copy_(terms["loss"].detach())
 
     def _capture(self, warmup_iters: int) -> None:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                      # warm-up off the default stream, as torch requires
-            for _ in range(warmup_iters):
-                self._body(device_hyper=True)
-        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(warmup_iters):                      # warm-up off the default stream, as torch requires
+            self._run_eager(device_hyper=True)
         torch.cuda.synchronize()
         steps_before = self.arena.step_count
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=self.stream):
             self._body(device_hyper=True)
         self.arena.step_count = steps_before               # capture advanced the host counter without running
 
@@ -117,5 +124,5 @@ class TrainStep:
             self.arena.stage_hyper(self.lr, self.betas[0], self.betas[1])     # pinned values read by the graph
             self.graph.replay()
         else:
-            self._body(device_hyper=False)
+            self._run_eager(device_hyper=False)
         return self.loss
