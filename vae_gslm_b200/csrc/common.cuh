@@ -72,6 +72,43 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// Fast GELU for the bf16 tensor-core epilogues: erf by Abramowitz–Stegun 7.1.26 (|error| <= 1.5e-7, far below
+// bf16 resolution) — one MUFU.RCP, one MUFU.EX2 and a 5-term Horner instead of erff's ~40 instructions.  The
+// exponential e^{-x^2/2} it needs is also the Gaussian density of GELU', so the derivative costs nothing extra.
+__device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z * 1.4426950408889634f));
+  e = ex;                                           // e^{-x^2/2}
+  const float erf_abs = 1.0f - poly * ex;           // erf(|x|/sqrt(2))
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, e;
+  gelu_fast_parts(x, cdf, e);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float cdf, e;
+  gelu_fast_parts(x, cdf, e);
+  return fmaf(x * 0.39894228040143268f, e, cdf);
+}
+__device__ __forceinline__ float apply_act_fast(float v, int act) {
+  if (act == VG_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == VG_ACT_GELU) return gelu_fast(v);
+  return v;
+}
+__device__ __forceinline__ float act_grad_fast(float pre, int act) {
+  if (act == VG_ACT_RELU) return pre > 0.f ? 1.f : 0.f;
+  if (act == VG_ACT_GELU) return gelu_grad_fast(pre);
+  return 1.f;
+}
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == VG_ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == VG_ACT_GELU) return gelu_f(v);

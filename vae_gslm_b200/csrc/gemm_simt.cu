@@ -105,26 +105,49 @@ int gemm_simt_launch(const vg_gemm_args* a, cudaStream_t st) {
 }
 
 // ---- column sums (bias gradients) ----------------------------------------------------------------
-constexpr int kColsumRowsPerBlock = 256;
+// stage 1: each thread owns 8 consecutive columns (one 16-byte load per row) and walks a strip of rows;
+// stage 2: fixed-order sum of the strip partials.  HBM-bound: the matrix is read exactly once.
+constexpr int kColsumRowsPerBlock = 64;
 
 template <typename T>
-__global__ void colsum_stage1(const T* __restrict__ x, int64_t ld, float* __restrict__ partial,
-                              int64_t rows, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+__global__ void __launch_bounds__(128)
+colsum_stage1(const T* __restrict__ x, int64_t ld, float* __restrict__ partial, int64_t rows, int cols) {
+  const int c0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (c0 >= cols) return;
   const int64_t r0 = (int64_t)blockIdx.y * kColsumRowsPerBlock;
   const int64_t r1 = r0 + kColsumRowsPerBlock < rows ? r0 + kColsumRowsPerBlock : rows;
-  float s = 0.f;
-  for (int64_t r = r0; r < r1; ++r) s += to_f32<T>(x[r * ld + c]);
-  partial[(int64_t)blockIdx.y * cols + c] = s;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const bool vec = (c0 + 8 <= cols) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int64_t r = r0; r < r1; ++r) {
+    if (vec) {
+      Vec8<T> v;
+      v.load(x + r * ld + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v.v[j];
+    } else {
+      for (int j = 0; j < 8 && c0 + j < cols; ++j) acc[j] += to_f32<T>(x[r * ld + c0 + j]);
+    }
+  }
+  for (int j = 0; j < 8 && c0 + j < cols; ++j) partial[(int64_t)blockIdx.y * cols + c0 + j] = acc[j];
 }
-__global__ void colsum_stage2(const float* __restrict__ partial, float* __restrict__ out, int nparts,
-                              int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+__global__ void __launch_bounds__(256)
+colsum_stage2(const float* __restrict__ partial, float* __restrict__ out, int nparts, int cols) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * cols + c];
-  out[c] = s;
+  if (c < cols)
+    for (int p = ty; p < nparts; p += 8) s += partial[(int64_t)p * cols + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][tx];
+    out[c] = t;
+  }
 }
 
 }  // namespace vg
@@ -144,13 +167,13 @@ extern "C" int vg_colsum(const void* x, int64_t ld, float* out, int64_t rows, in
              "vg_colsum: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int nparts = (int)ceil_div(rows, kColsumRowsPerBlock);
-  dim3 grid((unsigned)ceil_div(cols, 128), nparts), block(128);
+  dim3 grid((unsigned)ceil_div(cols, 1024), nparts), block(128);
   if (x_dtype == VG_F32)
     colsum_stage1<float><<<grid, block, 0, st>>>((const float*)x, ld, (float*)workspace, rows, (int)cols);
   else
     colsum_stage1<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ld, (float*)workspace, rows, (int)cols);
   VG_LAUNCH_CHECK("vg_colsum(stage1)");
-  colsum_stage2<<<(unsigned)ceil_div(cols, 128), 128, 0, st>>>((const float*)workspace, out, nparts, (int)cols);
+  colsum_stage2<<<(unsigned)ceil_div(cols, 32), 256, 0, st>>>((const float*)workspace, out, nparts, (int)cols);
   VG_LAUNCH_CHECK("vg_colsum(stage2)");
   return 0;
 }

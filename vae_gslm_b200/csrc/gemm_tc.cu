@@ -11,7 +11,8 @@
 //   warp 0 lane 0 : TMA producer           (smem ring of kStages {A,B} tiles, full/empty mbarriers)
 //   warp 1 lane 0 : tcgen05.mma issuer     (128 x BN x 16 per instruction, 4 per 64-wide k-block)
 //   warp 2        : TMEM allocator         (2 accumulator buffers of BN columns → epilogue overlap)
-//   warps 4..7    : epilogue               (thread = accumulator row; tcgen05.ld 32 columns at a time)
+//   warps 4..11   : epilogue               (thread = accumulator row; two warps per TMEM lane quadrant split the
+//                                           columns; tcgen05.ld 32 columns at a time; fast-erf GELU)
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "sm100.cuh"
@@ -21,7 +22,8 @@ using namespace sm100;
 
 constexpr int TBM = 128;            // tile rows  (UMMA M)
 constexpr int TBK = 64;             // k-block: 64 bf16 = 128 B = one swizzle atom
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;
+constexpr int TC_EPI_THREADS = 256;         // warps 4..11
 constexpr int A_TILE_BYTES = TBM * TBK * 2;   // 16 KB
 
 template <int BN> struct TcCfg {
@@ -63,13 +65,13 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpilogue& e, int m, in
       }
       if (ep.act != VG_ACT_NONE) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
+        for (int j = 0; j < 8; ++j) v[j] = apply_act_fast(v[j], ep.act);
       }
       if (ep.dact_src) {
         Vec8<TC> d;
         d.load(reinterpret_cast<const TC*>(ep.dact_src) + (int64_t)m * ep.ld_dact + n);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= act_grad(d.v[j], ep.dact);
+        for (int j = 0; j < 8; ++j) v[j] *= act_grad_fast(d.v[j], ep.dact);
       }
       if (!keep && ep.mask_first) {
 #pragma unroll
@@ -131,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], TC_EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -223,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m0 + wq * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = (warp >= 8 ? BN / 64 : 0); c < (warp >= 8 ? BN / 32 : BN / 64); ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), r);
         tmem_ld_wait();

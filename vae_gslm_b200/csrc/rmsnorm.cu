@@ -129,18 +129,28 @@ rmsnorm_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const fl
   }
 }
 
-__global__ void colsum_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
-                                       int nparts, int dim) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= dim) return;
+// out[c] = sum_p partial[p][c], fixed order (deterministic): 32 columns x 8 row-groups per CTA
+__global__ void __launch_bounds__(256)
+colsum_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int dim) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * dim + c];
-  out[c] = s;
+  if (c < dim)
+    for (int p = ty; p < nparts; p += 8) s += partial[(int64_t)p * dim + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < dim) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][tx];
+    out[c] = t;
+  }
 }
 
 static int rms_bwd_blocks(int64_t rows) {
   int64_t want = ceil_div(rows, kRmsWarps);
-  int64_t cap = (int64_t)kNumSMs * 4;
+  int64_t cap = (int64_t)kNumSMs * 2;
   return (int)(want < cap ? want : cap);
 }
 
@@ -178,7 +188,7 @@ static int launch_bwd(const void* dy, const void* x, const float* scale, const f
   else VG_RMS_BWD(8);
 #undef VG_RMS_BWD
   VG_LAUNCH_CHECK("vg_rmsnorm_bwd");
-  colsum_partials_kernel<<<(dim + 255) / 256, 256, 0, st>>>(partial, dscale, nb, dim);
+  colsum_partials_kernel<<<(dim + 31) / 32, 256, 0, st>>>(partial, dscale, nb, dim);
   VG_LAUNCH_CHECK("vg_rmsnorm_bwd(reduce)");
   return 0;
 }
