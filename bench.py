@@ -228,8 +228,16 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(result), flush=True)
     if world > 1:
+        # Tear-down: a CUDA graph that captured NCCL kernels keeps the communicator busy and
+        # destroy_process_group() was observed to hang behind it.  Synchronise, meet at a barrier, drop the graph and
+        # leave without the collective destructor (the line above is already flushed).
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        train_step.graph = None
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def decode_bench(model, dev, peaks, batches=(1, 64), prompt=150, steps=48):

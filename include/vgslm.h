@@ -29,7 +29,8 @@ extern "C" {
 typedef struct CUstream_st* vg_stream_t;
 
 typedef enum { VG_F32 = 0, VG_BF16 = 1 } vg_dtype;
-typedef enum { VG_ACT_NONE = 0, VG_ACT_RELU = 1, VG_ACT_GELU = 2 } vg_act;
+/* VG_ACT_MULT is valid for `dact` only: the saved tensor already holds act'(pre) and is simply multiplied in */
+typedef enum { VG_ACT_NONE = 0, VG_ACT_RELU = 1, VG_ACT_GELU = 2, VG_ACT_SILU = 3, VG_ACT_MULT = 4 } vg_act;
 typedef enum { VG_GEMM_AUTO = 0, VG_GEMM_SIMT = 1, VG_GEMM_TCGEN05 = 2 } vg_gemm_backend;
 
 #define VG_VERSION 100
@@ -82,6 +83,8 @@ typedef struct {
   const void* residual; int64_t ld_res;
   const uint8_t* row_mask;
   int32_t mask_before_residual;
+  int32_t preact_is_grad;   /* 1: `preact` receives act'(v) instead of v, so that backward is a plain multiply
+                               (VG_ACT_MULT) — the forward epilogue already has erf/exp of v in registers */
   float beta;
 } vg_gemm_args;
 size_t vg_gemm_workspace(const vg_gemm_args* a, int backend);
@@ -226,6 +229,27 @@ int vg_latent_back_bwd(const vg_latent_back_bwd_args* a, void* workspace, size_t
  * z0 = mean_p + exp(logstd_p)·eps·temperature ; z = Flow^{-1}(z0; FiLM columns of head). */
 int vg_latent_prior_sample(const vg_latent_back_args* a, const float* eps, float temperature,
                            float* z_out, vg_stream_t stream);
+
+/* ---- conv-stack front half of a ResidualBlock on [B,T,C] rows (the first "next" row):
+ * y = LayerNorm_C( depthwise_conv_k(x) + bias [+ t_add[b,:]] ) with zero padding at the array ends
+ * (conv/layers.py:13-31,117-135,238-253) and the UNBIASED-variance channel norm of norm.py:43-47.
+ * w_t is the depthwise weight transposed to [taps][C]; w_t == NULL means identity (plain channel LayerNorm, used
+ * for BottleNeckResNet.final_norm).  mean/rstd [B*T] are saved for backward.  The surrounding 1x1 convolutions are
+ * plain vg_gemm calls on the same [B*T, C] buffers.                                                          */
+int vg_dwconv_ln_fwd(const void* x, const float* w_t, const float* bias /* nullable */,
+                     const float* t_add /* [B,C] nullable */, const float* ln_w, const float* ln_b,
+                     void* y, int64_t ld_y, float* mean, float* rstd,
+                     int64_t B, int64_t T, int64_t C, int32_t taps, int32_t pad_left, float eps, int dtype,
+                     vg_stream_t stream);
+size_t vg_dwconv_ln_bwd_workspace(int64_t B, int64_t T, int64_t C, int32_t taps);
+/* dh = dL/d(conv output) [B,T,C] (the caller sums it over T for d t_add); dx = transposed depthwise conv of dh;
+ * dw_t [taps][C], d_ln_w, d_ln_b, d_bias [C] are overwritten (deterministic two-stage reduction).              */
+int vg_dwconv_ln_bwd(const void* dy, int64_t ld_dy, const void* x, const float* w_t, const float* bias,
+                     const float* t_add, const float* ln_w, const float* mean, const float* rstd,
+                     void* dh, void* dx, float* dw_t /* nullable iff w_t is NULL */, float* d_ln_w, float* d_ln_b,
+                     float* d_bias /* nullable */, void* workspace, size_t workspace_bytes,
+                     int64_t B, int64_t T, int64_t C, int32_t taps, int32_t pad_left, int dtype,
+                     vg_stream_t stream);
 
 /* ---- token cross-entropy: losses.py:30-41 (F.cross_entropy, ignore_index −100, reduction=sum)   */
 size_t vg_softmax_ce_workspace(int64_t rows);

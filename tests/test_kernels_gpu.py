@@ -133,6 +133,74 @@ def test_colsum():
     assert rel_err(ops.colsum(xb), xb.float().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,C,pad_left,timed,identity", [(2, 37, 512, 6, True, False), (3, 20, 16, 0, False, False),
+                                                           (2, 9, 64, 6, False, False), (2, 33, 512, 0, False, True)])
+def test_dwconv_ln_fwd_bwd(dtype, B, T, C, pad_left, timed, identity):
+    """fused depthwise conv (k=7, causal or future padded) + time-embedding add + channel LayerNorm (unbiased var)
+    against the reference formulation in B,C,T layout (conv/layers.py:238-253, norm.py:43-47)."""
+    k = 7
+    x = torch.randn(B, T, C, device=DEV).to(dtype).requires_grad_(True)
+    cw = None if identity else (0.3 * torch.randn(C, 1, k, device=DEV)).requires_grad_(True)
+    cb = None if identity else (0.1 * torch.randn(C, device=DEV)).requires_grad_(True)
+    ta = (0.5 * torch.randn(B, C, device=DEV)).requires_grad_(True) if timed else None
+    lw = (1 + 0.1 * torch.randn(C, device=DEV)).requires_grad_(True)
+    lb = (0.1 * torch.randn(C, device=DEV)).requires_grad_(True)
+    y = ops.dwconv_ln(x, cw, cb, ta, lw, lb, pad_left, 1e-6)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+
+    def clone(t):
+        return None if t is None else t.detach().float().clone().requires_grad_(True)
+    xr, cwr, cbr, tar, lwr, lbr = (clone(t) for t in (x, cw, cb, ta, lw, lb))
+    h = xr.transpose(1, 2)                                                     # B,C,T like the reference
+    if not identity:
+        h = torch.nn.functional.conv1d(torch.nn.functional.pad(h, (pad_left, k - 1 - pad_left)), cwr, cbr, groups=C)
+    if timed:
+        h = h + tar[..., None]
+    var, mean = torch.var_mean(h, dim=1, keepdim=True)
+    yr = (lwr[:, None] * ((h - mean) * torch.rsqrt(var + 1e-6)) + lbr[:, None]).transpose(1, 2)
+    yr.backward(gy.float())
+    t_ = 3e-2 if dtype == torch.bfloat16 else 2e-4
+    assert rel_err(y, yr) < t_
+    assert rel_err(x.grad, xr.grad) < t_
+    assert rel_err(lw.grad, lwr.grad) < t_ and rel_err(lb.grad, lbr.grad) < t_
+    if not identity:
+        assert rel_err(cw.grad, cwr.grad) < t_ and rel_err(cb.grad, cbr.grad) < t_
+    if timed:
+        assert rel_err(ta.grad, tar.grad) < t_
+
+
+def test_gemm_silu_and_stored_derivative():
+    """SiLU epilogue and the 'store act'(pre)' mode used by the backward of ops.linear / ops.ffn."""
+    M, N, K = 200, 264, 128
+    a = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    for be in (ops.GEMM_SIMT, ops.GEMM_TCGEN05):
+        for act, fn in ((ops.ACT_SILU, torch.nn.functional.silu), (ops.ACT_GELU, torch.nn.functional.gelu)):
+            d = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+            out = ops.gemm(a, w, bias=bias, act=act, preact=d, preact_is_grad=True, backend=be)
+            pre = (a.float() @ w.float().t() + bias).requires_grad_(True)
+            ref = fn(pre)
+            ref.sum().backward()
+            assert rel_err(out, ref) < 2e-2 and rel_err(d, pre.grad) < 2e-2
+            g = torch.randn(M, N, device=DEV).to(torch.bfloat16)
+            got = ops.act_bwd(g, d, ops.ACT_MULT)
+            assert rel_err(got, g.float() * d.float()) < 1e-2
+    # a Conv1d(k=1) weight [N,K,1] is accepted as a linear weight, gradients come back in its shape
+    x = torch.randn(3, 50, K, device=DEV, requires_grad=True)
+    w3 = (torch.randn(N, K, 1, device=DEV) / math.sqrt(K)).requires_grad_(True)
+    b = torch.randn(N, device=DEV, requires_grad=True)
+    y = ops.linear(x, w3, b, act=ops.ACT_SILU)
+    y.sum().backward()
+    xr, wr, br = (t.detach().clone().requires_grad_(True) for t in (x, w3, b))
+    torch.nn.functional.silu(torch.nn.functional.linear(xr, wr[..., 0], br)).sum().backward()
+    assert rel_err(y, torch.nn.functional.silu(torch.nn.functional.linear(xr, wr[..., 0], br))) < 1e-4
+    assert rel_err(w3.grad, wr.grad) < 1e-4 and rel_err(x.grad, xr.grad) < 1e-4 and rel_err(b.grad, br.grad) < 1e-4
+    assert w3.grad.shape == w3.shape
+
+
 # ------------------------------------------------------------------------------------ attention
 def _attn_ref(qkv, H, lengths, slopes, q_offset=0, k=None, v=None):
     B, Tq, C3 = qkv.shape

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgslm.so")
 
 VG_F32, VG_BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU, ACT_MULT = 0, 1, 2, 3, 4
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 
 _p = C.c_void_p
@@ -40,6 +40,7 @@ class GemmArgs(C.Structure):
         ("residual", _p), ("ld_res", _i64),
         ("row_mask", _p),
         ("mask_before_residual", _i32),
+        ("preact_is_grad", _i32),
         ("beta", _f32),
     ]
 
@@ -121,6 +122,11 @@ _SIGNATURES = {
     "vg_latent_back_fwd": (C.c_int, [C.POINTER(LatentBackArgs), _p, _sz, _p]),
     "vg_latent_back_bwd": (C.c_int, [C.POINTER(LatentBackBwdArgs), _p, _sz, _p]),
     "vg_latent_prior_sample": (C.c_int, [C.POINTER(LatentBackArgs), _p, _f32, _p, _p]),
+    "vg_dwconv_ln_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32,
+                                   C.c_int, _p]),
+    "vg_dwconv_ln_bwd_workspace": (_sz, [_i64, _i64, _i64, _i32]),
+    "vg_dwconv_ln_bwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
+                                   _i64, _i64, _i64, _i32, _i32, C.c_int, _p]),
     "vg_softmax_ce_workspace": (_sz, [_i64]),
     "vg_softmax_ce_fwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i64, C.c_int, _p, _sz, _p]),
     "vg_softmax_ce_bwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i64, C.c_int, _p]),

@@ -64,7 +64,7 @@ class _Group:
             self.p[o:o + n].copy_(p.detach().reshape(-1))
             p.data = self.p[o:o + n].view(p.shape)
             p.grad = self.g[o:o + n].view(p.shape)
-            if shadow and p.dim() == 2:
+            if shadow and p.dim() >= 2:
                 p._vg_shadow = self.shadow[o:o + n].view(p.shape)
         if shadow:
             L.call("vg_cast_f32_to_bf16", L.ptr(self.p), L.ptr(self.shadow), self.numel, L.stream())
@@ -87,11 +87,14 @@ class ParamArena:
         self._hyper_host = [torch.zeros(4, dtype=torch.float32).pin_memory() if torch.cuda.is_available()
                             else torch.zeros(4) for _ in self.groups]
         self.on_grad_ready = None     # dp.py installs a callback(param) here
-        # big transformer matrices: their wgrad GEMM writes the arena directly (ops._Linear / ops._FFN)
+        # big transformer matrices and the conv stacks' 1x1 convolutions: their wgrad GEMM writes the arena directly
+        # (ops._wgrad)
         self.direct: List[nn.Parameter] = []
         if direct_wgrad:
             for n, p in zip(self.decay.names, self.decay.params):
-                if n.startswith("transformer.0.layers.") and p.dim() == 2 or n == "transformer.0.linear.weight":
+                conv_1x1 = p.dim() == 3 and p.shape[-1] == 1 and n.startswith(("encoder.0.", "decoder.model.unet."))
+                if (n.startswith("transformer.0.layers.") and p.dim() == 2 or n == "transformer.0.linear.weight"
+                        or conv_1x1):
                     p._vg_main_grad = p.grad
                     p._vg_arena = self
                     self.direct.append(p)

@@ -99,24 +99,55 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   gelu_fast_parts(x, cdf, e);
   return fmaf(x * 0.39894228040143268f, e, cdf);
 }
+// SiLU (conv stack): x·σ(x);  d/dx = σ(x)·(1 + x·(1 − σ(x)))
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+__device__ __forceinline__ float silu_grad_f(float x) {
+  const float s = sigmoid_f(x);
+  return s * fmaf(x, 1.0f - s, 1.0f);
+}
+// activation and derivative from one evaluation (the forward epilogue can store either)
+__device__ __forceinline__ void act_and_grad_fast(float v, int act, float& y, float& dy) {
+  if (act == VG_ACT_RELU) { y = v > 0.f ? v : 0.f; dy = v > 0.f ? 1.f : 0.f; return; }
+  if (act == VG_ACT_GELU) {
+    float cdf, e;
+    gelu_fast_parts(v, cdf, e);
+    y = v * cdf;
+    dy = fmaf(v * 0.39894228040143268f, e, cdf);
+    return;
+  }
+  if (act == VG_ACT_SILU) {
+    float ex;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-v * 1.4426950408889634f));
+    const float s = __frcp_rn(1.0f + ex);
+    y = v * s;
+    dy = s * fmaf(v, 1.0f - s, 1.0f);
+    return;
+  }
+  y = v; dy = 1.f;
+}
 __device__ __forceinline__ float apply_act_fast(float v, int act) {
-  if (act == VG_ACT_RELU) return v > 0.f ? v : 0.f;
-  if (act == VG_ACT_GELU) return gelu_fast(v);
-  return v;
+  float y, dy;
+  act_and_grad_fast(v, act, y, dy);
+  return y;
 }
 __device__ __forceinline__ float act_grad_fast(float pre, int act) {
-  if (act == VG_ACT_RELU) return pre > 0.f ? 1.f : 0.f;
-  if (act == VG_ACT_GELU) return gelu_grad_fast(pre);
-  return 1.f;
+  if (act == VG_ACT_MULT) return pre;       // `pre` already holds the derivative
+  float y, dy;
+  act_and_grad_fast(pre, act, y, dy);
+  return dy;
 }
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == VG_ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == VG_ACT_GELU) return gelu_f(v);
+  if (act == VG_ACT_SILU) return silu_f(v);
   return v;
 }
 __device__ __forceinline__ float act_grad(float pre, int act) {
   if (act == VG_ACT_RELU) return pre > 0.f ? 1.f : 0.f;
   if (act == VG_ACT_GELU) return gelu_grad_f(pre);
+  if (act == VG_ACT_SILU) return silu_grad_f(pre);
+  if (act == VG_ACT_MULT) return pre;
   return 1.f;
 }
 

@@ -24,6 +24,14 @@ mask_rows_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* _
 
 template <typename T>
 __global__ void __launch_bounds__(256)
+mask_rows_scalar_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ y, int64_t rows, int cols) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  y[i] = mask[i / cols] ? x[i] : from_f32<T>(0.f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
 act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ src, T* __restrict__ dx, int64_t n8, int act) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
@@ -43,10 +51,19 @@ extern "C" int vg_mask_rows(const void* x, const uint8_t* row_mask, void* y, int
                             vg_stream_t stream) {
   VG_REQUIRE(x && row_mask && y, -1, "vg_mask_rows: null pointer");
   VG_REQUIRE(valid_dtype(dtype), -2, "vg_mask_rows: bad dtype");
-  VG_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0, -3, "vg_mask_rows: cols must be a positive multiple of 8");
-  VG_REQUIRE(aligned(x, 16) && aligned(y, 16), -4, "vg_mask_rows: unaligned");
-  const int64_t n = rows * (cols / 8);
+  VG_REQUIRE(rows > 0 && cols > 0, -3, "vg_mask_rows: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
+  if (cols % 8 != 0 || !aligned(x, 16) || !aligned(y, 16)) {      // narrow tensors (e.g. the 4-wide latent heads)
+    const int64_t total = rows * cols;
+    if (dtype == VG_F32)
+      mask_rows_scalar_kernel<float><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>((const float*)x, row_mask, (float*)y, rows, (int)cols);
+    else
+      mask_rows_scalar_kernel<__nv_bfloat16><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)x, row_mask, (__nv_bfloat16*)y, rows, (int)cols);
+    VG_LAUNCH_CHECK("vg_mask_rows(scalar)");
+    return 0;
+  }
+  const int64_t n = rows * (cols / 8);
   if (dtype == VG_F32)
     mask_rows_kernel<float><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const float*)x, row_mask, (float*)y, rows, (int)(cols / 8));
   else
@@ -60,7 +77,7 @@ extern "C" int vg_act_bwd(const void* dy, const void* src, void* dx, int64_t n, 
   VG_REQUIRE(dy && src && dx, -1, "vg_act_bwd: null pointer");
   VG_REQUIRE(valid_dtype(dtype), -2, "vg_act_bwd: bad dtype");
   VG_REQUIRE(n > 0 && n % 8 == 0, -3, "vg_act_bwd: n must be a positive multiple of 8");
-  VG_REQUIRE(act == VG_ACT_RELU || act == VG_ACT_GELU, -3, "vg_act_bwd: activation must be ReLU or GELU");
+  VG_REQUIRE(act >= VG_ACT_RELU && act <= VG_ACT_MULT, -3, "vg_act_bwd: activation must be ReLU, GELU, SiLU or MULT");
   VG_REQUIRE(aligned(dy, 16) && aligned(src, 16) && aligned(dx, 16), -4, "vg_act_bwd: unaligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VG_F32)

@@ -24,7 +24,7 @@ extern "C" int vg_gemm(const vg_gemm_args* a, int backend, void* /*workspace*/, 
   VG_REQUIRE(a->ldc >= a->N, -3, "vg_gemm: ldc too small");
   VG_REQUIRE(a->beta == 0.f || a->beta == 1.f, -3, "vg_gemm: beta must be 0 or 1");
   VG_REQUIRE(a->beta == 0.f || a->c_dtype == VG_F32, -3, "vg_gemm: beta=1 requires an f32 C");
-  VG_REQUIRE(a->act >= VG_ACT_NONE && a->act <= VG_ACT_GELU && a->dact >= VG_ACT_NONE && a->dact <= VG_ACT_GELU,
+  VG_REQUIRE(a->act >= VG_ACT_NONE && a->act <= VG_ACT_SILU && a->dact >= VG_ACT_NONE && a->dact <= VG_ACT_MULT,
              -3, "vg_gemm: bad activation id");
   VG_REQUIRE(!a->preact || a->ld_preact >= a->N, -3, "vg_gemm: ld_preact too small");
   VG_REQUIRE(!a->dact_src || a->ld_dact >= a->N, -3, "vg_gemm: ld_dact too small");

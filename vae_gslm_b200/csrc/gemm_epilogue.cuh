@@ -13,6 +13,7 @@ struct EpilogueParams {
   const void* residual; int64_t ld_res;
   const uint8_t* row_mask;
   int mask_first;
+  int preact_is_grad;
   float beta;
 };
 
@@ -26,6 +27,7 @@ static inline EpilogueParams make_epilogue(const vg_gemm_args* a) {
   ep.residual = a->residual; ep.ld_res = a->ld_res;
   ep.row_mask = a->row_mask;
   ep.mask_first = a->mask_before_residual;
+  ep.preact_is_grad = a->preact_is_grad;
   ep.beta = a->beta;
   return ep;
 }
@@ -34,7 +36,9 @@ static inline EpilogueParams make_epilogue(const vg_gemm_args* a) {
 template <typename TC>
 __device__ __forceinline__ void epilogue_store(const EpilogueParams& ep, int m, int n, float v) {
   if (ep.bias) v += ep.bias[n];
-  if (ep.preact) reinterpret_cast<TC*>(ep.preact)[(int64_t)m * ep.ld_preact + n] = from_f32<TC>(v);
+  if (ep.preact)
+    reinterpret_cast<TC*>(ep.preact)[(int64_t)m * ep.ld_preact + n] =
+        from_f32<TC>(ep.preact_is_grad ? act_grad(v, ep.act) : v);
   v = apply_act(v, ep.act);
   if (ep.dact_src)
     v *= act_grad(to_f32<TC>(reinterpret_cast<const TC*>(ep.dact_src)[(int64_t)m * ep.ld_dact + n]), ep.dact);

@@ -57,15 +57,16 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpilogue& e, int m, in
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] += b.v[j];
       }
-      if (ep.preact) {
+      if (ep.act != VG_ACT_NONE || ep.preact) {
         Vec8<TC> p;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) p.v[j] = v[j];
-        p.store(reinterpret_cast<TC*>(ep.preact) + (int64_t)m * ep.ld_preact + n);
-      }
-      if (ep.act != VG_ACT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = apply_act_fast(v[j], ep.act);
+        for (int j = 0; j < 8; ++j) {
+          float y, dy;
+          act_and_grad_fast(v[j], ep.act, y, dy);
+          p.v[j] = ep.preact_is_grad ? dy : v[j];
+          v[j] = y;
+        }
+        if (ep.preact) p.store(reinterpret_cast<TC*>(ep.preact) + (int64_t)m * ep.ld_preact + n);
       }
       if (ep.dact_src) {
         Vec8<TC> d;

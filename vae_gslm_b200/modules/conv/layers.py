@@ -1,11 +1,16 @@
-"""Convolutional blocks of the posterior encoder, the utterance encoder and the diffusion UNet
+"""Convolutional blocks of the posterior encoder, the diffusion UNet and the utterance encoder
 (reference ``modules/conv/layers.py``: Conv1d :13-31, ResidualBlock family :70-295,
 BottleNeckResNet :386-540, ConvNormAct / CNNStack :543-652).
 
-These sit inside the training step but outside the four kernel groups the north star names; this round
-they remain torch/cuDNN calls (SURVEY §8f-1 lists them as the first "next" row).  The classes keep the
-reference's parameter names so checkpoints load, and its quirk that activations in padded frames are
-NOT zeroed between blocks.
+SURVEY §8f-1 (first "next" row) — the residual blocks now run on libvgslm:
+  * activations stay ``[B,T,C]`` (the reference transposes to B,C,T for cuDNN and back);
+  * ``norm(conv1(x) [+ time_emb])`` — depthwise k=7 conv (causal or future padded) + channel "InstanceNorm" — is ONE
+    fused kernel (``ops.dwconv_ln``);
+  * the 1x1 convolutions ``conv2`` / ``conv3`` / ``skip_conv`` are plain GEMMs on the same rows (``ops.linear`` with
+    the Conv1d weight ``[N,K,1]`` viewed as ``[N,K]``), with bias + ReLU/SiLU and the residual add fused in the epilogue.
+Parameter names/shapes are the reference's (checkpoints load unchanged).  Its quirk that activations in padded frames
+are NOT zeroed between blocks is kept.  The small utterance encoder (strided convs over ≤200
+frames) stays on torch/cuDNN.
 """
 from __future__ import annotations
 
@@ -15,12 +20,12 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ... import ops
 from ...hparams.hp import Hparams
 from ...utils.helpers import get_padding
 from ...utils.tensormask import TensorMask
 from ..activations import get_activation
-from ..linear.layers import FiLM
-from ..norm import get_norm_fn
+from ..norm import InstanceNorm, get_norm_fn
 
 
 class Conv1d(nn.Conv1d):
@@ -42,7 +47,7 @@ class Conv1d(nn.Conv1d):
 
 
 class ResidualBlock(nn.Module):
-    """depthwise k-conv → channel norm → 1x1 up → act → 1x1 down → + x   (B,C,T layout)."""
+    """x + conv3(act(conv2([norm(conv1(x) + t) ; cond])))  on a B,T,C TensorMask."""
 
     def __init__(self, hp: Hparams):
         super().__init__()
@@ -53,21 +58,28 @@ class ResidualBlock(nn.Module):
         ch = hp.in_channels
         padding = get_padding(hp.kernel_size, causal=hp.get("causal_padding", False),
                               future=hp.get("future_padding", False))
+        self.pad_left = padding[0] if isinstance(padding, tuple) else padding
         self.norm = get_norm_fn(ch, hp.norm)
+        if not isinstance(self.norm, InstanceNorm):
+            raise NotImplementedError("the fused conv block implements the channel 'InstanceNorm' of the configuration")
         self.act = get_activation(hp.activation)
+        self._act_id = ops.ACT_IDS.get(hp.activation.identifier)
+        if self._act_id is None:
+            raise NotImplementedError(f"activation {hp.activation.identifier} is not fused (ReLU / GELU / SiLU are)")
         self.conv1 = Conv1d(ch, ch, kernel_size=hp.kernel_size, padding=padding, groups=ch)
         self.conv2 = nn.Conv1d(ch + hp.get("aux_in_channels", 0), hp.hidden_channels, kernel_size=1)
         self.conv3 = nn.Conv1d(hp.hidden_channels, ch, kernel_size=1)
 
-    def _body(self, x: TensorMask, pre_norm_add=None, cond: Optional[torch.Tensor] = None) -> TensorMask:
-        h = self.conv1(x.value)
-        if pre_norm_add is not None:
-            h = h + pre_norm_add
-        h = self.norm(h)
+    def _body(self, x: TensorMask, t_add: Optional[torch.Tensor] = None,
+              cond: Optional[torch.Tensor] = None) -> TensorMask:
+        xv = x.value
+        h = ops.dwconv_ln(xv, self.conv1.weight, self.conv1.bias, t_add, self.norm.weight, self.norm.bias,
+                          self.pad_left, self.norm.eps)
         if cond is not None:
-            h = torch.cat([h, cond.to(h.dtype)], 1)
-        h = self.conv3(self.act(self.conv2(h)))
-        return TensorMask(h + x.value, x.mask, axis=2)
+            h = torch.cat([h, cond.to(h.dtype)], -1)
+        a = ops.linear(h, self.conv2.weight, self.conv2.bias, act=self._act_id)
+        y = ops.linear(a, self.conv3.weight, self.conv3.bias, residual=xv)
+        return TensorMask(y, x.mask)
 
     def forward(self, x: TensorMask) -> TensorMask:
         return self._body(x)
@@ -96,7 +108,7 @@ class TemporalResidualBlock(ResidualBlock):
         self.time_emb = nn.Linear(hp.time_dim, hp.in_channels)
 
     def forward(self, x: TensorMask, t: torch.Tensor) -> TensorMask:
-        return self._body(x, pre_norm_add=self.time_emb(self.act(t))[..., None])
+        return self._body(x, t_add=self.time_emb(self.act(t.float())))
 
 
 class TCResidualBlock(ResidualBlock):
@@ -107,12 +119,12 @@ class TCResidualBlock(ResidualBlock):
         self.time_emb = nn.Linear(hp.time_dim, hp.in_channels)
 
     def forward(self, x: TensorMask, c: TensorMask, t: torch.Tensor) -> TensorMask:
-        return self._body(x, pre_norm_add=self.time_emb(self.act(t))[..., None], cond=c.value)
+        return self._body(x, t_add=self.time_emb(self.act(t.float())), cond=c.value)
 
 
 class BottleNeckResNet(nn.Module):
     """Linear in → N residual blocks (optionally time/condition aware, with UNet-style skips) →
-    channel norm → Linear out.  Input/output are B,T,C TensorMasks."""
+    channel norm → Linear out.  Input/output are B,T,C TensorMasks; nothing is transposed."""
 
     def __init__(self, hp: Hparams, input_dim: Optional[int] = None, output_dim: Optional[int] = None) -> None:
         super().__init__()
@@ -157,31 +169,41 @@ class BottleNeckResNet(nn.Module):
         self.linear = nn.Linear(input_dim, hp.init_channel) if input_dim is not None else None
         self.out_linear = nn.Linear(hp.out_channels[-1], output_dim) if output_dim is not None else None
         self.final_norm = get_norm_fn(hp.out_channels[-1], hp.layer.norm) if hp.get("final_norm", False) else None
-        self.first_norm = get_norm_fn(hp.layer.in_channels, hp.layer.norm) if hp.get("first_norm", False) else None
+        if hp.get("first_norm", False):
+            raise NotImplementedError("first_norm is unused by the VAE-GSLM configuration")
+        self.first_norm = None
+        self.compute_dtype = torch.float32          # set by LVTR.set_compute_dtype
 
     def forward(self, x: TensorMask, c: Optional[TensorMask] = None, t: Optional[torch.Tensor] = None) -> TensorMask:
+        mask = x.mask
+        h = x.value.to(self.compute_dtype)
         if self.linear is not None:
-            x = TensorMask(self.linear(x.value), x.mask).apply_mask()
-        x = x.transpose()
-        if self.first_norm is not None:
-            x = TensorMask(self.first_norm(x.value), x.mask, axis=2)
-        c = c.transpose() if c is not None else None
-        records = [x]
-        for layer, cond, skip, merge in zip(self.layers, self.conditional, self.skip_connection, self.skip_conv):
-            args = ([c] if cond else []) + ([t] if self.time_dim is not None else [])
-            x = layer(x, *args)
+            h = ops.linear(h, self.linear.weight, self.linear.bias, row_mask=mask)
+        cur = TensorMask(h, mask)
+        cond = TensorMask(c.value.to(self.compute_dtype), c.mask) if c is not None else None
+        records = [cur]
+        for layer, is_cond, skip, merge in zip(self.layers, self.conditional, self.skip_connection, self.skip_conv):
+            args = ([cond] if is_cond else []) + ([t] if self.time_dim is not None else [])
+            cur = layer(cur, *args)
             if skip is not None:
                 if self.skip_concat:
-                    x = TensorMask(merge(torch.cat([x.value, records[skip].value], 1)), x.mask, axis=2)
+                    both = torch.cat([cur.value, records[skip].value], -1)
+                    cur = TensorMask(ops.linear(both, merge.weight, merge.bias), mask)
                 else:
-                    x = x + records[skip]
-            records.append(x)
+                    cur = cur + records[skip]
+            records.append(cur)
+        h = cur.value
         if self.final_norm is not None:
-            x = TensorMask(self.final_norm(x.value), x.mask, axis=2)
-        x = x.transpose()
-        if self.out_linear is not None:
-            x = TensorMask(self.out_linear(x.value), x.mask).apply_mask()
-        return x.apply_mask()
+            h = ops.dwconv_ln(h, None, None, None, self.final_norm.weight, self.final_norm.bias, 0,
+                              self.final_norm.eps)
+        if self.out_linear is not None and self.out_linear.out_features < 8:
+            # 512 → 4 projection of the posterior encoder: too narrow for the GEMM tiles, a 16 KB weight — torch
+            h = torch.where(mask[..., None], F.linear(h.float(), self.out_linear.weight, self.out_linear.bias), 0.0)
+        elif self.out_linear is not None:
+            h = ops.linear(h, self.out_linear.weight, self.out_linear.bias, row_mask=mask)
+        else:
+            h = ops.mask_rows(h, mask)
+        return TensorMask(h, mask)
 
     @property
     def sample_ratio(self) -> float:
@@ -192,7 +214,7 @@ class BottleNeckResNet(nn.Module):
 
 
 class ConvNormAct(nn.Module):
-    """(strided) conv → channel norm → activation.
+    """(strided) conv → channel norm → activation (torch/cuDNN, B,C,T).
 
     Reference quirk kept on purpose (layers.py:576,591-593): ``self.stride`` holds 1/stride and the valid
     length is resized by 1/self.stride = stride, so after a stride-2 layer the recorded length DOUBLES

@@ -35,9 +35,11 @@ class ConditionalBottleNeckUNet(nn.Module):
 
     def forward(self, noise: TensorMask, t: torch.Tensor, cond: TensorMask) -> TensorMask:
         """noise, cond: [B,T,C]; t: [B] diffusion step indices."""
+        from ... import ops
         temb = self.time_embedding(t)
-        cond = TensorMask(self.cond_net(cond.value.to(self.cond_net.weight.dtype)), cond.mask).apply_mask()
-        return self.unet(noise, cond, temb)
+        c = ops.linear(cond.value.to(self.unet.compute_dtype), self.cond_net.weight, self.cond_net.bias,
+                       row_mask=cond.mask)                       # Linear + apply_mask in one GEMM epilogue
+        return self.unet(noise, TensorMask(c, cond.mask), temb)
 
 
 class ConditionalUNet(nn.Module):

@@ -12,15 +12,15 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05
+from ._lib import ACT_GELU, ACT_MULT, ACT_NONE, ACT_RELU, ACT_SILU, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05
 
 # GEMM backend used for bf16 operands: AUTO picks tcgen05 when the shape qualifies.
 GEMM_BACKEND = GEMM_AUTO
 # when a list, every bf16 GEMM launch appends (start_event, end_event, flops, dtype) — bench.py's roofline probe
 PROFILE = None
 
-ACT_IDS = {"none": ACT_NONE, None: ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU,
-           "ReLU": ACT_RELU, "GELU": ACT_GELU}
+ACT_IDS = {"none": ACT_NONE, None: ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "silu": ACT_SILU,
+           "ReLU": ACT_RELU, "GELU": ACT_GELU, "SiLU": ACT_SILU}
 
 
 def _u8(mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -80,7 +80,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          preact: Optional[torch.Tensor] = None, dact_src: Optional[torch.Tensor] = None, dact: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, row_mask: Optional[torch.Tensor] = None,
-         mask_first: bool = False, beta: float = 0.0, backend: Optional[int] = None) -> torch.Tensor:
+         mask_first: bool = False, beta: float = 0.0, backend: Optional[int] = None,
+         preact_is_grad: bool = False) -> torch.Tensor:
     """C = epilogue(op(A)·op(B)); see vg_gemm in include/vgslm.h.  ``a``/``b`` are 2-D with unit inner stride."""
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     assert a.dtype == b.dtype, (a.dtype, b.dtype)
@@ -116,6 +117,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
         assert row_mask.numel() == M
         g.row_mask = L.ptr(row_mask)
     g.mask_before_residual = int(mask_first)
+    g.preact_is_grad = int(preact_is_grad)
     g.beta = beta
     be = GEMM_BACKEND if backend is None else backend
     prof = PROFILE if (PROFILE is not None and a.dtype == torch.bfloat16) else None
@@ -215,10 +217,10 @@ def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor) -> Optiona
     main = getattr(weight, "_vg_main_grad", None)
     if main is not None:
         arena = weight._vg_arena
-        gemm(dy2, x2, trans_a=True, trans_b=False, out=main, beta=arena.wgrad_beta())
+        gemm(dy2, x2, trans_a=True, trans_b=False, out=main.view(main.shape[0], -1), beta=arena.wgrad_beta())
         arena.grad_ready(weight)
         return None
-    dw = gemm(dy2, x2, trans_a=True, trans_b=False, out_dtype=torch.float32)
+    dw = gemm(dy2, x2, trans_a=True, trans_b=False, out_dtype=torch.float32).view(weight.shape)   # 1x1 conv: [N,K,1]
     return dw if weight.dtype == torch.float32 else dw.to(weight.dtype)
 
 
@@ -229,15 +231,19 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, x, weight, bias, residual, mask_u8, act, mask_first, out_dtype, w_compute):
         x2 = _rows2d(x)
         w = w_compute if w_compute is not None else lowp(weight, x2.dtype)
+        if w.dim() == 3:                       # kernel-size-1 Conv1d weight [N,K,1] used as a linear layer
+            w = w.view(w.shape[0], -1)
         N = w.shape[0]
         odt = out_dtype or x2.dtype
         res2 = _rows2d(residual) if residual is not None else None
         b = bias.detach().float() if bias is not None else None
-        need_pre = act != ACT_NONE and (act == ACT_GELU or residual is not None or mask_u8 is not None)
+        # ReLU's derivative can be read off the output; otherwise the epilogue stores act'(pre) next to act(pre)
+        need_pre = act != ACT_NONE and (act != ACT_RELU or residual is not None or mask_u8 is not None)
         pre = torch.empty((x2.shape[0], N), dtype=odt, device=x.device) if need_pre else None
-        y = gemm(x2, w, trans_b=True, out_dtype=odt, bias=b, act=act, preact=pre, residual=res2,
+        y = gemm(x2, w, trans_b=True, out_dtype=odt, bias=b, act=act, preact=pre, preact_is_grad=True, residual=res2,
                  row_mask=mask_u8, mask_first=mask_first)
         ctx.save_for_backward(x2, w, pre if need_pre else (y if act != ACT_NONE else None), mask_u8)
+        ctx.act_bwd = ACT_MULT if need_pre else act
         ctx.meta = (act, mask_first, x.shape, weight, bias is not None, residual is not None,
                     residual.shape if residual is not None else None)
         return y.view(*x.shape[:-1], N)
@@ -251,7 +257,7 @@ class _Linear(torch.autograd.Function):
         dres = None
         if has_res and ctx.needs_input_grad[3]:
             dres = (dy2 if mask_first else g).view(res_shape)
-        dpre = act_bwd(g, act_src, act) if act != ACT_NONE else g
+        dpre = act_bwd(g, act_src, ctx.act_bwd) if act != ACT_NONE else g
         if dpre.dtype != x2.dtype:           # fp32 head outputs of bf16 GEMMs
             dpre = dpre.to(x2.dtype)
         dx = dw = db = None
@@ -284,7 +290,8 @@ class _FFN(torch.autograd.Function):
         w1c, w2c = lowp(w1, x2.dtype), lowp(w2, x2.dtype)
         M, F = x2.shape[0], w1c.shape[0]
         pre = torch.empty((M, F), dtype=x2.dtype, device=x.device)
-        h = gemm(x2, w1c, trans_b=True, bias=b1.detach().float() if b1 is not None else None, act=act, preact=pre)
+        h = gemm(x2, w1c, trans_b=True, bias=b1.detach().float() if b1 is not None else None, act=act, preact=pre,
+                 preact_is_grad=True)          # `pre` holds act'(W1·x + b1): backward is a plain multiply
         res2 = _rows2d(residual) if residual is not None else None
         y = gemm(h, w2c, trans_b=True, bias=b2.detach().float() if b2 is not None else None, residual=res2,
                  row_mask=mask_u8)
@@ -299,7 +306,7 @@ class _FFN(torch.autograd.Function):
         dy2 = _rows2d(dy).contiguous()
         g = mask_rows_(dy2, mask_u8) if mask_u8 is not None else dy2
         dres = g.view(dy.shape) if has_res and ctx.needs_input_grad[5] else None
-        dpre = gemm(g, w2c, trans_b=False, dact_src=pre, dact=act)            # (g·W2) ⊙ act'(pre)
+        dpre = gemm(g, w2c, trans_b=False, dact_src=pre, dact=ACT_MULT)       # (g·W2) ⊙ act'(pre), saved by forward
         dw2 = _wgrad(g, h, w2) if ctx.needs_input_grad[3] else None
         db2 = colsum(g) if has_b2 and ctx.needs_input_grad[4] else None
         dx = gemm(dpre, w1c, trans_b=False).view(xshape) if ctx.needs_input_grad[0] else None
@@ -310,6 +317,63 @@ class _FFN(torch.autograd.Function):
 
 def ffn(x, w1, b1, w2, b2, residual=None, row_mask=None, act: int = ACT_GELU) -> torch.Tensor:
     return _FFN.apply(x, w1, b1, w2, b2, residual, _u8(row_mask), act)
+
+
+# ------------------------------------------------------------------------- depthwise conv + channel LN
+class _DwConvLN(torch.autograd.Function):
+    """norm(conv1(x) [+ time_emb]) of a ResidualBlock on [B,T,C] rows (conv/layers.py:117-135,238-253; norm.py:43-47)."""
+
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, t_add, ln_w, ln_b, pad_left, eps, out_cols):
+        B, T, Cc = x.shape
+        xc = x.contiguous()
+        if conv_w is not None:
+            taps = conv_w.shape[-1]
+            w_t = conv_w.detach().reshape(Cc, taps).t().contiguous().float()         # [taps][C]
+        else:
+            taps, w_t = 1, None
+        cb = _f32c(conv_b)
+        ta = _f32c(t_add)
+        lw, lb = _f32c(ln_w), _f32c(ln_b)
+        ld_y = out_cols or Cc                 # the caller may ask for a wider row (room for concatenated conditions)
+        y = torch.empty((B, T, ld_y), dtype=x.dtype, device=x.device)
+        mean = torch.empty(B * T, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(B * T, dtype=torch.float32, device=x.device)
+        L.call("vg_dwconv_ln_fwd", L.ptr(xc), L.ptr(w_t), L.ptr(cb), L.ptr(ta), L.ptr(lw), L.ptr(lb), L.ptr(y), ld_y,
+               L.ptr(mean), L.ptr(rstd), B, T, Cc, taps, int(pad_left), float(eps), L.dtype_id(x.dtype), L.stream())
+        ctx.save_for_backward(xc, w_t, cb, ta, lw, mean, rstd)
+        ctx.meta = (taps, int(pad_left), conv_w.shape if conv_w is not None else None, conv_b is not None,
+                    t_add is not None, ld_y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, w_t, cb, ta, lw, mean, rstd = ctx.saved_tensors
+        taps, pad_left, w_shape, has_b, has_t, ld_y = ctx.meta
+        B, T, Cc = xc.shape
+        dyc = dy.contiguous()                                  # [B,T,ld_y]; only the first C columns are ours
+        dev = xc.device
+        dh = torch.empty_like(xc)
+        dx = torch.empty_like(xc)
+        f32 = dict(dtype=torch.float32, device=dev)
+        dw_t = torch.empty((taps, Cc), **f32) if w_t is not None else None
+        dlw, dlb = torch.empty(Cc, **f32), torch.empty(Cc, **f32)
+        db = torch.empty(Cc, **f32) if has_b else None
+        ws = L.workspace(L.load().vg_dwconv_ln_bwd_workspace(B, T, Cc, taps), dev)
+        L.call("vg_dwconv_ln_bwd", L.ptr(dyc), ld_y, L.ptr(xc), L.ptr(w_t), L.ptr(cb), L.ptr(ta), L.ptr(lw),
+               L.ptr(mean), L.ptr(rstd), L.ptr(dh), L.ptr(dx), L.ptr(dw_t), L.ptr(dlw), L.ptr(dlb), L.ptr(db),
+               L.ptr(ws), ws.numel(), B, T, Cc, taps, pad_left, L.dtype_id(xc.dtype), L.stream())
+        dconv_w = dw_t.t().reshape(w_shape) if w_t is not None else None
+        dt = dh.sum(1, dtype=torch.float32) if has_t else None
+        return dx, dconv_w, db, dt, dlw, dlb, None, None, None
+
+
+def dwconv_ln(x: torch.Tensor, conv_w: Optional[torch.Tensor], conv_b: Optional[torch.Tensor],
+              t_add: Optional[torch.Tensor], ln_w: torch.Tensor, ln_b: torch.Tensor, pad_left: int, eps: float,
+              out_cols: Optional[int] = None) -> torch.Tensor:
+    """x [B,T,C] → LayerNorm_C(depthwise_conv(x) + bias + t_add[:,None,:]); conv_w [C,1,k] or None (identity).
+    With ``out_cols`` > C the result has that many columns and only [:C] is written."""
+    return _DwConvLN.apply(x, conv_w, conv_b, t_add, ln_w, ln_b, pad_left, eps, out_cols)
 
 
 # -------------------------------------------------------------------------------------- attention
