@@ -47,10 +47,13 @@ int vg_rmsnorm_fwd(const void* x, const float* scale, const uint8_t* row_mask /*
                    void* y, float* rstd, int64_t rows, int64_t dim, float eps,
                    int x_dtype, int y_dtype, vg_stream_t stream);
 size_t vg_rmsnorm_bwd_workspace(int64_t rows, int64_t dim);
-/* dx = (dres ? dres : 0) + d/dx ; dscale[dim] overwritten (deterministic two-stage reduction). */
+/* dx = (dres ? dres : 0) + d/dx  (dres: the gradient arriving through the residual branch that bypasses the norm,
+ * transformer/layers.py:57,63 — fused here instead of a separate add);
+ * dscale[dim] = dscale_beta * dscale + sum_rows(...)  (deterministic two-stage reduction; beta = 1 accumulates
+ * straight into a gradient buffer). */
 int vg_rmsnorm_bwd(const void* dy, const void* x, const float* scale, const float* rstd,
                    const uint8_t* row_mask /* nullable */, const void* dres /* nullable */,
-                   void* dx, float* dscale, void* workspace, size_t workspace_bytes,
+                   void* dx, float* dscale, float dscale_beta, void* workspace, size_t workspace_bytes,
                    int64_t rows, int64_t dim, int x_dtype, int dy_dtype, vg_stream_t stream);
 
 /* ---- GEMM with fused epilogue: every nn.Linear on the path
@@ -90,9 +93,9 @@ typedef struct {
 size_t vg_gemm_workspace(const vg_gemm_args* a, int backend);
 int    vg_gemm(const vg_gemm_args* a, int backend, void* workspace, size_t workspace_bytes,
                vg_stream_t stream);
-/* column sums: out[n] = sum_m X[m,n] (bias gradients), deterministic. */
+/* column sums: out[n] = beta * out[n] + sum_m X[m,n] (bias gradients), deterministic; beta in {0,1}. */
 size_t vg_colsum_workspace(int64_t rows, int64_t cols);
-int    vg_colsum(const void* x, int64_t ld, float* out, int64_t rows, int64_t cols, int x_dtype,
+int    vg_colsum(const void* x, int64_t ld, float* out, int64_t rows, int64_t cols, int x_dtype, float beta,
                  void* workspace, size_t workspace_bytes, vg_stream_t stream);
 
 /* ---- small elementwise helpers used by the backward passes

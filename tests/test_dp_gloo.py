@@ -47,8 +47,10 @@ def test_arena_layout(golden):
     assert len(buckets) > 3
     assert sum(len(m) for _, m in buckets) == len(params)
     assert sum(b.numel() for b, _ in buckets) == arena.total_numel()
-    # only non-direct gradients need zeroing; direct ones are the big transformer matrices
-    assert all(p.dim() in (2, 3) for p in arena.direct) and len(arena.direct) >= 2 * 4 + 1
+    # only non-direct gradients need zeroing; direct ones are the big transformer matrices, the conv stacks' 1x1
+    # convolutions and the transformer layers' biases / RMSNorm scales (written by the GEMM / colsum / norm kernels)
+    assert all(p.dim() in (1, 2, 3) for p in arena.direct) and len(arena.direct) >= 2 * 4 + 1
+    assert sum(p.dim() == 1 for p in arena.direct) >= 2
 
 
 def _worker(rank, world, port, fixture_path, result_q):

@@ -126,6 +126,25 @@ def test_gemm_tcgen05_layouts(trans_a, trans_b, M, N, K):
     assert rel_err(out16, ref) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 200, 4096), (1024, 1024, 8000), (384, 512, 2048)])
+def test_gemm_tcgen05_split_k(M, N, K):
+    """wgrad-shaped GEMMs (f32 C, long K, few tiles) run split-K with red.global.add partial sums: beta = 0 clears C
+    first (also through a strided view), beta = 1 accumulates into it."""
+    a = torch.randn(K, M, device=DEV).to(torch.bfloat16)
+    b = torch.randn(K, N, device=DEV).to(torch.bfloat16)
+    ref = a.float().t() @ b.float()
+    out = torch.full((M, N), 7.0, device=DEV)
+    ops.gemm(a, b, trans_a=True, trans_b=False, out=out, backend=ops.GEMM_TCGEN05)
+    assert rel_err(out, ref) < 2e-3
+    wide = torch.full((M, N + 24), 3.0, device=DEV)
+    ops.gemm(a, b, trans_a=True, trans_b=False, out=wide[:, :N], backend=ops.GEMM_TCGEN05)
+    assert rel_err(wide[:, :N], ref) < 2e-3 and bool((wide[:, N:] == 3.0).all())
+    acc = torch.randn(M, N, device=DEV)
+    ref2 = acc + ref
+    ops.gemm(a, b, trans_a=True, trans_b=False, out=acc, beta=1.0, backend=ops.GEMM_TCGEN05)
+    assert rel_err(acc, ref2) < 2e-3
+
+
 def test_colsum():
     x = torch.randn(1000, 520, device=DEV)
     assert rel_err(ops.colsum(x), x.sum(0)) < 1e-5

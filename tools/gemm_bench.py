@@ -7,7 +7,10 @@ import torch
 from vae_gslm_b200 import ops
 
 dev = "cuda"
-M = int(sys.argv[1]) if len(sys.argv) > 1 else 8000
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+M = int(args[0]) if args else 8000
+WGRAD_ONLY = "--wgrad-only" in sys.argv
+QUICK = "--quick" in sys.argv or WGRAD_ONLY
 bf = torch.bfloat16
 
 
@@ -32,18 +35,29 @@ def report(name, flops, ours, ref):
 x1k = torch.randn(M, 1024, device=dev).to(bf)
 x4k = torch.randn(M, 4096, device=dev).to(bf)
 mask = torch.ones(M, dtype=torch.uint8, device=dev)
-for (N, K, tag) in [(3072, 1024, "qkv"), (1024, 1024, "out_proj"), (4096, 1024, "ffn1"), (1024, 4096, "ffn2"),
-                    (2048, 1024, "spliters"), (520, 1024, "head"), (200, 1024, "logits"), (1024, 64, "stack_in")]:
+SHAPES = [(3072, 1024, "qkv"), (1024, 1024, "out_proj"), (4096, 1024, "ffn1"), (1024, 4096, "ffn2")]
+if not QUICK:
+    SHAPES += [(2048, 1024, "spliters"), (520, 1024, "head"), (200, 1024, "logits"), (1024, 64, "stack_in"),
+               (2048, 544, "conv_up"), (512, 2048, "conv_down")]
+for (N, K, tag) in SHAPES:
     x = torch.randn(M, K, device=dev).to(bf)
     w = (torch.randn(N, K, device=dev) / K ** 0.5).to(bf)
     dy = torch.randn(M, N, device=dev).to(bf)
     fl = 2.0 * M * N * K
+    acc = torch.zeros(N, K, device=dev)
+    report(f"wgrad+= {tag} [{N},{M}]x[{M},{K}] f32 beta=1", fl,
+           timeit(lambda: ops.gemm(dy, x, trans_a=True, trans_b=False, out=acc, beta=1.0)),
+           timeit(lambda: dy.t() @ x))
+    if WGRAD_ONLY:
+        continue
     report(f"fwd   {tag} [{M},{K}]x[{N},{K}]T", fl, timeit(lambda: ops.gemm(x, w)), timeit(lambda: x @ w.t()))
     report(f"dgrad {tag} [{M},{N}]x[{N},{K}]", fl, timeit(lambda: ops.gemm(dy, w, trans_b=False)),
            timeit(lambda: dy @ w))
     report(f"wgrad {tag} [{N},{M}]x[{M},{K}]", fl,
            timeit(lambda: ops.gemm(dy, x, trans_a=True, trans_b=False, out_dtype=torch.float32)),
            timeit(lambda: dy.t() @ x))
+if WGRAD_ONLY:
+    sys.exit(0)
 # fused-epilogue variants actually used by the layer
 w1 = (torch.randn(4096, 1024, device=dev) / 32).to(bf)
 b1 = torch.randn(4096, device=dev)
@@ -57,3 +71,8 @@ report("fwd ffn2 +bias+res+mask", 2.0 * M * 4096 * 1024,
 dy1k = torch.randn(M, 1024, device=dev).to(bf)
 report("dgrad ffn2 * gelu'(pre)", 2.0 * M * 4096 * 1024,
        timeit(lambda: ops.gemm(dy1k, w2, trans_b=False, dact_src=pre, dact=ops.ACT_GELU)), timeit(lambda: dy1k @ w2))
+report("fwd ffn1 +bias+gelu+gelu'(pre) saved", 2.0 * M * 4096 * 1024,
+       timeit(lambda: ops.gemm(x1k, w1, bias=b1, act=ops.ACT_GELU, preact=pre, preact_is_grad=True)),
+       timeit(lambda: x1k @ w1.t()))
+report("dgrad ffn2 * saved derivative", 2.0 * M * 4096 * 1024,
+       timeit(lambda: ops.gemm(dy1k, w2, trans_b=False, dact_src=pre, dact=ops.ACT_MULT)), timeit(lambda: dy1k @ w2))

@@ -97,11 +97,11 @@ _SIGNATURES = {
     "vg_device_is_sm100": (C.c_int, []),
     "vg_rmsnorm_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _f32, C.c_int, C.c_int, _p]),
     "vg_rmsnorm_bwd_workspace": (_sz, [_i64, _i64]),
-    "vg_rmsnorm_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i64, _i64, C.c_int, C.c_int, _p]),
+    "vg_rmsnorm_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _f32, _p, _sz, _i64, _i64, C.c_int, C.c_int, _p]),
     "vg_gemm_workspace": (_sz, [C.POINTER(GemmArgs), C.c_int]),
     "vg_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_int, _p, _sz, _p]),
     "vg_colsum_workspace": (_sz, [_i64, _i64]),
-    "vg_colsum": (C.c_int, [_p, _i64, _p, _i64, _i64, C.c_int, _p, _sz, _p]),
+    "vg_colsum": (C.c_int, [_p, _i64, _p, _i64, _i64, C.c_int, _f32, _p, _sz, _p]),
     "vg_mask_rows": (C.c_int, [_p, _p, _p, _i64, _i64, C.c_int, _p]),
     "vg_act_bwd": (C.c_int, [_p, _p, _p, _i64, C.c_int, C.c_int, _p]),
     "vg_attn_fwd": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p,

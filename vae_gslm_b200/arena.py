@@ -98,6 +98,13 @@ class ParamArena:
                     p._vg_main_grad = p.grad
                     p._vg_arena = self
                     self.direct.append(p)
+            # biases and RMSNorm scales of the transformer layers: ops._bgrad / the RMSNorm backward kernel write
+            # (beta = 0) or accumulate (beta = 1) their gradient slice directly — no AccumulateGrad add kernels
+            for n, p in zip(self.nodecay.names, self.nodecay.params):
+                if n.startswith("transformer.0.layers.") or n == "transformer.0.final_norm.scale":
+                    p._vg_main_grad = p.grad
+                    p._vg_arena = self
+                    self.direct.append(p)
         direct_ids = {id(p) for p in self.direct}
         # contiguous runs of NON-direct gradients: only those need zeroing before backward
         self._zero_runs: List[torch.Tensor] = []

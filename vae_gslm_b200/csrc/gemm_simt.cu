@@ -107,7 +107,7 @@ int gemm_simt_launch(const vg_gemm_args* a, cudaStream_t st) {
 // ---- column sums (bias gradients) ----------------------------------------------------------------
 // stage 1: each thread owns 8 consecutive columns (one 16-byte load per row) and walks a strip of rows;
 // stage 2: fixed-order sum of the strip partials.  HBM-bound: the matrix is read exactly once.
-constexpr int kColsumRowsPerBlock = 64;
+constexpr int kColsumRowsPerBlock = 32;
 
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -120,20 +120,32 @@ colsum_stage1(const T* __restrict__ x, int64_t ld, float* __restrict__ partial, 
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   const bool vec = (c0 + 8 <= cols) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  for (int64_t r = r0; r < r1; ++r) {
-    if (vec) {
+  if (vec) {
+    // 8 independent 16-byte loads in flight per thread (the row loop is otherwise latency-bound), fixed add order
+    int64_t r = r0;
+    for (; r + 8 <= r1; r += 8) {
+      Vec8<T> v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u].load(x + (r + u) * ld + c0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u].v[j];
+    }
+    for (; r < r1; ++r) {
       Vec8<T> v;
       v.load(x + r * ld + c0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v.v[j];
-    } else {
-      for (int j = 0; j < 8 && c0 + j < cols; ++j) acc[j] += to_f32<T>(x[r * ld + c0 + j]);
     }
+  } else {
+    for (int64_t r = r0; r < r1; ++r)
+      for (int j = 0; j < 8 && c0 + j < cols; ++j) acc[j] += to_f32<T>(x[r * ld + c0 + j]);
   }
   for (int j = 0; j < 8 && c0 + j < cols; ++j) partial[(int64_t)blockIdx.y * cols + c0 + j] = acc[j];
 }
 __global__ void __launch_bounds__(256)
-colsum_stage2(const float* __restrict__ partial, float* __restrict__ out, int nparts, int cols) {
+colsum_stage2(const float* __restrict__ partial, float* __restrict__ out, int nparts, int cols, float beta) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -146,7 +158,7 @@ colsum_stage2(const float* __restrict__ partial, float* __restrict__ out, int np
     float t = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) t += red[g][tx];
-    out[c] = t;
+    out[c] = beta != 0.f ? fmaf(beta, out[c], t) : t;
   }
 }
 
@@ -159,7 +171,7 @@ extern "C" size_t vg_colsum_workspace(int64_t rows, int64_t cols) {
 }
 
 extern "C" int vg_colsum(const void* x, int64_t ld, float* out, int64_t rows, int64_t cols,
-                         int x_dtype, void* workspace, size_t workspace_bytes, vg_stream_t stream) {
+                         int x_dtype, float beta, void* workspace, size_t workspace_bytes, vg_stream_t stream) {
   VG_REQUIRE(x && out, -1, "vg_colsum: null pointer");
   VG_REQUIRE(valid_dtype(x_dtype), -2, "vg_colsum: bad dtype");
   VG_REQUIRE(rows > 0 && cols > 0 && ld >= cols, -3, "vg_colsum: bad shape");
@@ -173,7 +185,7 @@ extern "C" int vg_colsum(const void* x, int64_t ld, float* out, int64_t rows, in
   else
     colsum_stage1<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ld, (float*)workspace, rows, (int)cols);
   VG_LAUNCH_CHECK("vg_colsum(stage1)");
-  colsum_stage2<<<(unsigned)ceil_div(cols, 32), 256, 0, st>>>((const float*)workspace, out, nparts, (int)cols);
+  colsum_stage2<<<(unsigned)ceil_div(cols, 32), 256, 0, st>>>((const float*)workspace, out, nparts, (int)cols, beta);
   VG_LAUNCH_CHECK("vg_colsum(stage2)");
   return 0;
 }

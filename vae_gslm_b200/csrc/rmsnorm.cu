@@ -131,7 +131,7 @@ rmsnorm_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const fl
 
 // out[c] = sum_p partial[p][c], fixed order (deterministic): 32 columns x 8 row-groups per CTA
 __global__ void __launch_bounds__(256)
-colsum_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int dim) {
+colsum_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int dim, float beta) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -144,13 +144,13 @@ colsum_partials_kernel(const float* __restrict__ partial, float* __restrict__ ou
     float t = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) t += red[g][tx];
-    out[c] = t;
+    out[c] = beta != 0.f ? fmaf(beta, out[c], t) : t;
   }
 }
 
 static int rms_bwd_blocks(int64_t rows) {
   int64_t want = ceil_div(rows, kRmsWarps);
-  int64_t cap = (int64_t)kNumSMs * 2;
+  int64_t cap = (int64_t)kNumSMs * 4;      // 16 warps per SM: enough rows in flight to cover HBM latency
   return (int)(want < cap ? want : cap);
 }
 
@@ -173,8 +173,8 @@ static int launch_fwd(const void* x, const float* scale, const uint8_t* mask, vo
 
 template <typename TX, typename TG>
 static int launch_bwd(const void* dy, const void* x, const float* scale, const float* rstd,
-                      const uint8_t* mask, const void* dres, void* dx, float* dscale, float* partial,
-                      int64_t rows, int dim, cudaStream_t st) {
+                      const uint8_t* mask, const void* dres, void* dx, float* dscale, float dscale_beta,
+                      float* partial, int64_t rows, int dim, cudaStream_t st) {
   const int iters = (dim + 255) / 256;
   const int nb = rms_bwd_blocks(rows);
   dim3 grid(nb), block(kRmsWarps * 32);
@@ -188,7 +188,7 @@ static int launch_bwd(const void* dy, const void* x, const float* scale, const f
   else VG_RMS_BWD(8);
 #undef VG_RMS_BWD
   VG_LAUNCH_CHECK("vg_rmsnorm_bwd");
-  colsum_partials_kernel<<<(dim + 31) / 32, 256, 0, st>>>(partial, dscale, nb, dim);
+  colsum_partials_kernel<<<(dim + 31) / 32, 256, 0, st>>>(partial, dscale, nb, dim, dscale_beta);
   VG_LAUNCH_CHECK("vg_rmsnorm_bwd(reduce)");
   return 0;
 }
@@ -224,7 +224,7 @@ extern "C" size_t vg_rmsnorm_bwd_workspace(int64_t rows, int64_t dim) {
 
 extern "C" int vg_rmsnorm_bwd(const void* dy, const void* x, const float* scale, const float* rstd,
                               const uint8_t* row_mask, const void* dres, void* dx, float* dscale,
-                              void* workspace, size_t workspace_bytes, int64_t rows, int64_t dim,
+                              float dscale_beta, void* workspace, size_t workspace_bytes, int64_t rows, int64_t dim,
                               int x_dtype, int dy_dtype, vg_stream_t stream) {
   VG_REQUIRE(dy && x && scale && rstd && dx && dscale, -1, "vg_rmsnorm_bwd: null pointer");
   VG_REQUIRE(valid_dtype(x_dtype) && valid_dtype(dy_dtype), -2, "vg_rmsnorm_bwd: bad dtype");
@@ -237,10 +237,10 @@ extern "C" int vg_rmsnorm_bwd(const void* dy, const void* x, const float* scale,
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = (float*)workspace;
   if (x_dtype == VG_F32 && dy_dtype == VG_F32)
-    return launch_bwd<float, float>(dy, x, scale, rstd, row_mask, dres, dx, dscale, partial, rows, (int)dim, st);
+    return launch_bwd<float, float>(dy, x, scale, rstd, row_mask, dres, dx, dscale, dscale_beta, partial, rows, (int)dim, st);
   if (x_dtype == VG_BF16 && dy_dtype == VG_BF16)
-    return launch_bwd<__nv_bfloat16, __nv_bfloat16>(dy, x, scale, rstd, row_mask, dres, dx, dscale, partial, rows, (int)dim, st);
+    return launch_bwd<__nv_bfloat16, __nv_bfloat16>(dy, x, scale, rstd, row_mask, dres, dx, dscale, dscale_beta, partial, rows, (int)dim, st);
   if (x_dtype == VG_BF16 && dy_dtype == VG_F32)
-    return launch_bwd<__nv_bfloat16, float>(dy, x, scale, rstd, row_mask, dres, dx, dscale, partial, rows, (int)dim, st);
-  return launch_bwd<float, __nv_bfloat16>(dy, x, scale, rstd, row_mask, dres, dx, dscale, partial, rows, (int)dim, st);
+    return launch_bwd<__nv_bfloat16, float>(dy, x, scale, rstd, row_mask, dres, dx, dscale, dscale_beta, partial, rows, (int)dim, st);
+  return launch_bwd<float, __nv_bfloat16>(dy, x, scale, rstd, row_mask, dres, dx, dscale, dscale_beta, partial, rows, (int)dim, st);
 }

@@ -22,6 +22,14 @@ from ..norm import RMSNorm, get_norm_fn
 from ..position.embedding import get_positional_encoding
 
 
+def _norm_with_residual(norm: nn.Module, x: torch.Tensor, mask: Optional[torch.Tensor]):
+    """(residual input, norm(x)) of a pre-LN block.  For RMSNorm the residual is an autograd alias of x whose
+    gradient is added inside the fused RMSNorm backward kernel (ops.rmsnorm_residual) instead of a separate add."""
+    if isinstance(norm, RMSNorm) and torch.is_grad_enabled() and x.requires_grad:
+        return ops.rmsnorm_residual(x, norm.scale, norm.eps, mask)
+    return x, _apply_norm(norm, x, mask)
+
+
 def _apply_norm(norm: nn.Module, x: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
     if isinstance(norm, RMSNorm):
         return norm(x, mask)
@@ -62,11 +70,11 @@ class TransformerLayer(nn.Module):
         output = dict()
         x, mask = tgt.value, tgt.mask
         if self.preln:
-            n = TensorMask(_apply_norm(self.norm1, x, mask), mask)
-            sa = self.self_attn(n, past_kv=past_kv, rpe_pair=rpe_pair, rpe_bias=rpe_bias,
-                                return_attn=return_attn, return_kv=return_kv, _residual=x)
-            h1 = sa["output"].value                                   # x + mask(attn)
-            out = self._ffn(_apply_norm(self.norm3, h1, None), h1, mask)
+            x_res, n1 = _norm_with_residual(self.norm1, x, mask)
+            sa = self.self_attn(TensorMask(n1, mask), past_kv=past_kv, rpe_pair=rpe_pair, rpe_bias=rpe_bias,
+                                return_attn=return_attn, return_kv=return_kv, _residual=x_res)
+            h1_res, n3 = _norm_with_residual(self.norm3, sa["output"].value, None)   # sa output = x + mask(attn)
+            out = self._ffn(n3, h1_res, mask)
         else:
             sa = self.self_attn(tgt, past_kv=past_kv, rpe_pair=rpe_pair, rpe_bias=rpe_bias,
                                 return_attn=return_attn, return_kv=return_kv, _residual=x)

@@ -131,13 +131,29 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
     return out
 
 
-def colsum(x: torch.Tensor) -> torch.Tensor:
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, beta: float = 0.0) -> torch.Tensor:
+    """out[n] = beta·out[n] + Σ_m x[m,n] (bias gradients)."""
     rows, cols = x.shape
-    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    if out is None:
+        assert beta == 0.0
+        out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    assert out.dtype == torch.float32 and out.numel() == cols and out.is_contiguous()
     ws = L.workspace(L.load().vg_colsum_workspace(rows, cols), x.device)
-    L.call("vg_colsum", L.ptr(x), x.stride(0), L.ptr(out), rows, cols, L.dtype_id(x.dtype), L.ptr(ws), ws.numel(),
-           L.stream())
+    L.call("vg_colsum", L.ptr(x), x.stride(0), L.ptr(out), rows, cols, L.dtype_id(x.dtype), float(beta), L.ptr(ws),
+           ws.numel(), L.stream())
     return out
+
+
+def _bgrad(dy2: torch.Tensor, bias: torch.Tensor) -> Optional[torch.Tensor]:
+    """db = Σ_rows dy.  A bias that lives in a ParamArena gets the sum written (or accumulated, on later
+    micro-batches) straight into its gradient slice and autograd receives None — no AccumulateGrad add kernel."""
+    main = getattr(bias, "_vg_main_grad", None)
+    if main is not None:
+        arena = bias._vg_arena
+        colsum(dy2, out=main, beta=arena.wgrad_beta())
+        arena.grad_ready(bias)
+        return None
+    return colsum(dy2)
 
 
 def mask_rows_(x2: torch.Tensor, mask_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -176,10 +192,15 @@ def mask_rows(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
 
 # ---------------------------------------------------------------------------------------- RMSNorm
 class _RMSNorm(torch.autograd.Function):
-    """modules/norm.py:22-32 (+ the mask of transformer/layers.py:53-54)."""
+    """modules/norm.py:22-32 (+ the mask of transformer/layers.py:53-54).
+
+    With ``passthrough`` the function also returns its input (as an alias): a pre-LN block uses that alias as the
+    residual branch, so the two gradients of x — through the norm and around it — meet HERE and the backward kernel
+    adds them (``dres``) instead of autograd launching a separate add (transformer/layers.py:57,63)."""
 
     @staticmethod
-    def forward(ctx, x, scale, eps, mask_u8, out_dtype):
+    def forward(ctx, x, scale, eps, mask_u8, out_dtype, passthrough):
+        ctx.set_materialize_grads(False)
         x2 = _rows2d(x).contiguous()
         rows, dim = x2.shape
         y = torch.empty((rows, dim), dtype=out_dtype or x.dtype, device=x.device)
@@ -189,25 +210,51 @@ class _RMSNorm(torch.autograd.Function):
                L.dtype_id(x2.dtype), L.dtype_id(y.dtype), L.stream())
         ctx.save_for_backward(x2, sc, rstd, mask_u8)
         ctx.xshape = x.shape
+        ctx.scale_param = scale
+        ctx.passthrough = passthrough
+        if passthrough:
+            return x.view_as(x), y.view(x.shape)
         return y.view(x.shape)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, *grads):
         x2, sc, rstd, mask_u8 = ctx.saved_tensors
+        dres, dy = (grads[0], grads[1]) if ctx.passthrough else (None, grads[0])
+        if dy is None:                      # the normalised branch is unused: only the residual gradient flows
+            return dres, None, None, None, None, None
         rows, dim = x2.shape
         dy2 = _rows2d(dy).contiguous()
+        dres2 = None
+        if dres is not None:
+            dres2 = _rows2d(dres).contiguous()
+            if dres2.dtype != x2.dtype:
+                dres2 = dres2.to(x2.dtype)
         dx = torch.empty_like(x2)
-        dscale = torch.empty(dim, dtype=torch.float32, device=x2.device)
+        scale = ctx.scale_param
+        main = getattr(scale, "_vg_main_grad", None)
+        if main is not None:
+            dscale, beta = main, scale._vg_arena.wgrad_beta()
+        else:
+            dscale, beta = torch.empty(dim, dtype=torch.float32, device=x2.device), 0.0
         ws = L.workspace(L.load().vg_rmsnorm_bwd_workspace(rows, dim), x2.device)
-        L.call("vg_rmsnorm_bwd", L.ptr(dy2), L.ptr(x2), L.ptr(sc), L.ptr(rstd), L.ptr(mask_u8), None, L.ptr(dx),
-               L.ptr(dscale), L.ptr(ws), ws.numel(), rows, dim, L.dtype_id(x2.dtype), L.dtype_id(dy2.dtype),
-               L.stream())
-        return dx.view(ctx.xshape), dscale, None, None, None
+        L.call("vg_rmsnorm_bwd", L.ptr(dy2), L.ptr(x2), L.ptr(sc), L.ptr(rstd), L.ptr(mask_u8), L.ptr(dres2),
+               L.ptr(dx), L.ptr(dscale), float(beta), L.ptr(ws), ws.numel(), rows, dim, L.dtype_id(x2.dtype),
+               L.dtype_id(dy2.dtype), L.stream())
+        if main is not None:
+            scale._vg_arena.grad_ready(scale)
+            dscale = None
+        return dx.view(ctx.xshape), dscale, None, None, None, None
 
 
 def rmsnorm(x: torch.Tensor, scale: torch.Tensor, eps: float, mask: Optional[torch.Tensor] = None,
             out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    return _RMSNorm.apply(x, scale, eps, _u8(mask), out_dtype)
+    return _RMSNorm.apply(x, scale, eps, _u8(mask), out_dtype, False)
+
+
+def rmsnorm_residual(x: torch.Tensor, scale: torch.Tensor, eps: float, mask: Optional[torch.Tensor] = None,
+                     out_dtype: Optional[torch.dtype] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(x, RMSNorm(x)): use the returned x as the residual input of the block that consumes the norm."""
+    return _RMSNorm.apply(x, scale, eps, _u8(mask), out_dtype, True)
 
 
 # ----------------------------------------------------------------------------------------- Linear
@@ -244,14 +291,14 @@ class _Linear(torch.autograd.Function):
                  row_mask=mask_u8, mask_first=mask_first)
         ctx.save_for_backward(x2, w, pre if need_pre else (y if act != ACT_NONE else None), mask_u8)
         ctx.act_bwd = ACT_MULT if need_pre else act
-        ctx.meta = (act, mask_first, x.shape, weight, bias is not None, residual is not None,
+        ctx.meta = (act, mask_first, x.shape, weight, bias, residual is not None,
                     residual.shape if residual is not None else None)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, dy):
         x2, w, act_src, mask_u8 = ctx.saved_tensors
-        act, mask_first, xshape, weight, has_bias, has_res, res_shape = ctx.meta
+        act, mask_first, xshape, weight, bias, has_res, res_shape = ctx.meta
         dy2 = _rows2d(dy).contiguous()
         g = mask_rows_(dy2, mask_u8) if mask_u8 is not None else dy2
         dres = None
@@ -265,8 +312,8 @@ class _Linear(torch.autograd.Function):
             dx = gemm(dpre, w, trans_b=False).view(xshape)
         if ctx.needs_input_grad[1]:
             dw = _wgrad(dpre, x2, weight)
-        if has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dpre)
+        if bias is not None and ctx.needs_input_grad[2]:
+            db = _bgrad(dpre, bias)
         return dx, dw, db, dres, None, None, None, None, None
 
 
@@ -296,22 +343,22 @@ class _FFN(torch.autograd.Function):
         y = gemm(h, w2c, trans_b=True, bias=b2.detach().float() if b2 is not None else None, residual=res2,
                  row_mask=mask_u8)
         ctx.save_for_backward(x2, w1c, w2c, pre, h, mask_u8)
-        ctx.meta = (act, x.shape, b1 is not None, b2 is not None, residual is not None, w1, w2)
+        ctx.meta = (act, x.shape, b1, b2, residual is not None, w1, w2)
         return y.view(x.shape[:-1] + (w2c.shape[0],))
 
     @staticmethod
     def backward(ctx, dy):
         x2, w1c, w2c, pre, h, mask_u8 = ctx.saved_tensors
-        act, xshape, has_b1, has_b2, has_res, w1, w2 = ctx.meta
+        act, xshape, b1, b2, has_res, w1, w2 = ctx.meta
         dy2 = _rows2d(dy).contiguous()
         g = mask_rows_(dy2, mask_u8) if mask_u8 is not None else dy2
         dres = g.view(dy.shape) if has_res and ctx.needs_input_grad[5] else None
         dpre = gemm(g, w2c, trans_b=False, dact_src=pre, dact=ACT_MULT)       # (g·W2) ⊙ act'(pre), saved by forward
         dw2 = _wgrad(g, h, w2) if ctx.needs_input_grad[3] else None
-        db2 = colsum(g) if has_b2 and ctx.needs_input_grad[4] else None
+        db2 = _bgrad(g, b2) if b2 is not None and ctx.needs_input_grad[4] else None
         dx = gemm(dpre, w1c, trans_b=False).view(xshape) if ctx.needs_input_grad[0] else None
         dw1 = _wgrad(dpre, x2, w1) if ctx.needs_input_grad[1] else None
-        db1 = colsum(dpre) if has_b1 and ctx.needs_input_grad[2] else None
+        db1 = _bgrad(dpre, b1) if b1 is not None and ctx.needs_input_grad[2] else None
         return dx, dw1, db1, dw2, db2, dres, None, None
 
 
