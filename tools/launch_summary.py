@@ -12,7 +12,7 @@ for row in csv.DictReader(lines):
     rows.append((row['Kernel Name'], float(row['Metric Value'])))
 ad = [i for i, (n, _) in enumerate(rows) if 'adamw' in n]
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-step = rows[ad[2 * k - 1] + 1: ad[2 * k + 1] + 1] if len(ad) >= 2 * k + 2 else rows
+step = rows[ad[2 * k - 1] + 1: ad[2 * k + 1] + 1] if len(ad) >= 2 * k + 2 else rows[ad[-3] + 1: ad[-1] + 1]
 tot = sum(v for _, v in step)
 print(f'launches {len(step)}  total {tot / 1e6:.3f} ms (cold-cache, serialised)')
 

@@ -87,50 +87,28 @@ class ParamArena:
         self._hyper_host = [torch.zeros(4, dtype=torch.float32).pin_memory() if torch.cuda.is_available()
                             else torch.zeros(4) for _ in self.groups]
         self.on_grad_ready = None     # dp.py installs a callback(param) here
-        # big transformer matrices and the conv stacks' 1x1 convolutions: their wgrad GEMM writes the arena directly
-        # (ops._wgrad)
+        # Every parameter carries a handle to its gradient slice: the ops that produce parameter gradients on the hot
+        # path (wgrad GEMMs, bias column sums, RMSNorm scale sums — ops._wgrad / ops._bgrad / ops._RMSNorm) ACCUMULATE
+        # into it directly (beta = 1) and hand autograd None, so no AccumulateGrad add kernel runs for them.
+        # Gradients that still come back through autograd (torch ops, the fused latent / conv kernels) are added into
+        # the same slice by autograd itself.  Both are accumulations, hence one whole-arena clear per step.
         self.direct: List[nn.Parameter] = []
         if direct_wgrad:
-            for n, p in zip(self.decay.names, self.decay.params):
-                conv_1x1 = p.dim() == 3 and p.shape[-1] == 1 and n.startswith(("encoder.0.", "decoder.model.unet."))
-                if (n.startswith("transformer.0.layers.") and p.dim() == 2 or n == "transformer.0.linear.weight"
-                        or conv_1x1):
+            for grp in self.groups:
+                for p in grp.params:
                     p._vg_main_grad = p.grad
                     p._vg_arena = self
                     self.direct.append(p)
-            # biases and RMSNorm scales of the transformer layers: ops._bgrad / the RMSNorm backward kernel write
-            # (beta = 0) or accumulate (beta = 1) their gradient slice directly — no AccumulateGrad add kernels
-            for n, p in zip(self.nodecay.names, self.nodecay.params):
-                if n.startswith("transformer.0.layers.") or n == "transformer.0.final_norm.scale":
-                    p._vg_main_grad = p.grad
-                    p._vg_arena = self
-                    self.direct.append(p)
-        direct_ids = {id(p) for p in self.direct}
-        # contiguous runs of NON-direct gradients: only those need zeroing before backward
-        self._zero_runs: List[torch.Tensor] = []
-        for grp in self.groups:
-            run_start = None
-            for i, p in enumerate(grp.params):
-                o, n = grp.slice_of(i)
-                end = grp.offsets[i + 1] if i + 1 < len(grp.params) else grp.numel
-                if id(p) in direct_ids:
-                    if run_start is not None:
-                        self._zero_runs.append(grp.g[run_start:o])
-                        run_start = None
-                elif run_start is None:
-                    run_start = o
-                if i + 1 == len(grp.params) and run_start is not None:
-                    self._zero_runs.append(grp.g[run_start:end])
 
     # ------------------------------------------------------------------ per-step protocol
     def zero_grad(self) -> None:
-        """gradients the autograd engine accumulates into are zeroed; direct-wgrad slices are overwritten (beta=0)."""
-        for run in self._zero_runs:
-            run.zero_()
+        """one memset per arena (0.9 GB at HBM speed ≈ 0.15 ms); every producer accumulates afterwards."""
+        for grp in self.groups:
+            grp.g.zero_()
         self.micro_batch = 0
 
     def wgrad_beta(self) -> float:
-        return 0.0 if self.micro_batch == 0 else 1.0
+        return 1.0
 
     def end_micro_batch(self) -> None:
         self.micro_batch += 1

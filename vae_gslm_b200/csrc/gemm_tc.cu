@@ -90,7 +90,7 @@ bool gemm_tc_supported(const vg_gemm_args* a) {
 // epilogue is a pure f32 accumulation (wgrad into the gradient arena): partial tiles are reduced with
 // red.global.add, which costs ~2.5 us per unit of L2 atomic traffic — so it only pays when the tile count alone
 // leaves SMs idle (e.g. 32 tiles of the 1024x1024 out_proj wgrad on 148 SMs).
-struct TcPlan { int bn, splits; };
+struct TcPlan { int bn, splits, pair; };
 
 static bool splitk_eligible(const vg_gemm_args* a) {
   return a->c_dtype == VG_F32 && !a->bias && a->act == VG_ACT_NONE && !a->preact && !a->dact_src && !a->residual &&
@@ -102,8 +102,9 @@ static TcPlan pick_plan(const vg_gemm_args* a) {
   static const int env_splits = getenv("VG_GEMM_SPLITS") ? atoi(getenv("VG_GEMM_SPLITS")) : 0;
   const int64_t num_kb = ceil_div(a->K, TBK);
   const bool can_split = splitk_eligible(a);
-  if (a->N <= 64) return TcPlan{64, 1};
-  TcPlan best{128, 1};
+  static const int env_pair = getenv("VG_GEMM_PAIR") ? atoi(getenv("VG_GEMM_PAIR")) : 1;
+  if (a->N <= 64) return TcPlan{64, 1, 0};
+  TcPlan best{128, 1, 0};
   double best_cost = 1e30;
   for (int bn = 128; bn <= 256; bn *= 2) {
     if (bn == 256 && a->N < 256) continue;
@@ -117,9 +118,11 @@ static TcPlan pick_plan(const vg_gemm_args* a) {
       if (s > 1 && kbpu < 8) break;
       const int64_t waves = ceil_div(tiles * s, kNumSMs);
       const double cost = (double)waves * ((double)kbpu * per_kb + (s > 1 ? 2.5 : 0.0));
-      if (cost < best_cost * 0.97) { best_cost = cost; best = TcPlan{bn, s}; }   // ties → fewer splits / smaller BN
+      if (cost < best_cost * 0.97) { best_cost = cost; best = TcPlan{bn, s, 0}; }   // ties → fewer splits / smaller BN
     }
   }
+  // CTA pairs (cta_group::2, 256 x 256 tiles): same tile count per SM as 128 x 256, half the B traffic per SM
+  if (env_pair && best.bn == 256 && a->M >= 256) best.pair = 1;
   return best;
 }
 
@@ -131,7 +134,7 @@ int gemm_tc_launch(const vg_gemm_args* a, cudaStream_t st) {
   if (!a->trans_a) rc = make_tmap_bf16_2d(&tmA, a->A, a->K, a->M, a->lda, TBK, TBM);
   else             rc = make_tmap_bf16_2d(&tmA, a->A, a->M, a->K, a->lda, 64, TBK);
   if (rc) return rc;
-  if (a->trans_b)  rc = make_tmap_bf16_2d(&tmB, a->B, a->K, a->N, a->ldb, TBK, bn);
+  if (a->trans_b)  rc = make_tmap_bf16_2d(&tmB, a->B, a->K, a->N, a->ldb, TBK, plan.pair ? bn / 2 : bn);
   else             rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, 64, TBK);
   if (rc) return rc;
 
@@ -160,10 +163,12 @@ int gemm_tc_launch(const vg_gemm_args* a, cudaStream_t st) {
 
   const bool a_mn = a->trans_a != 0;      // stored [K,M] → M contiguous
   const bool b_mn = a->trans_b == 0;      // stored [K,N] → N contiguous
-  if (!a_mn && !b_mn) return gemm_tc_launch_kk(bn, tmA, tmB, a, epi, st);
-  if (!a_mn && b_mn) return gemm_tc_launch_kmn(bn, tmA, tmB, a, epi, st);
-  if (a_mn && !b_mn) return gemm_tc_launch_mnk(bn, tmA, tmB, a, epi, st);
-  return gemm_tc_launch_mnmn(bn, tmA, tmB, a, epi, st);
+  const int cfg = plan.pair ? 512 : bn;   // 512 selects the CTA-pair instantiation (256 x 256 tiles)
+  const bool f32 = a->c_dtype == VG_F32;
+  if (!a_mn && !b_mn) return f32 ? gemm_tc_launch_kk_f32(cfg, tmA, tmB, a, epi, st) : gemm_tc_launch_kk_bf16(cfg, tmA, tmB, a, epi, st);
+  if (!a_mn && b_mn) return f32 ? gemm_tc_launch_kmn_f32(cfg, tmA, tmB, a, epi, st) : gemm_tc_launch_kmn_bf16(cfg, tmA, tmB, a, epi, st);
+  if (a_mn && !b_mn) return f32 ? gemm_tc_launch_mnk_f32(cfg, tmA, tmB, a, epi, st) : gemm_tc_launch_mnk_bf16(cfg, tmA, tmB, a, epi, st);
+  return f32 ? gemm_tc_launch_mnmn_f32(cfg, tmA, tmB, a, epi, st) : gemm_tc_launch_mnmn_bf16(cfg, tmA, tmB, a, epi, st);
 }
 
 }  // namespace vg

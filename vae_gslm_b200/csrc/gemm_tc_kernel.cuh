@@ -14,10 +14,12 @@ constexpr int TC_THREADS = 640;
 constexpr int TC_EPI_THREADS = 512;         // warps 4..19: four per TMEM lane quadrant, each a quarter of the columns
 constexpr int A_TILE_BYTES = TBM * TBK * 2;   // 16 KB
 
-template <int BN> struct TcCfg {
-  static constexpr int kBBytes = BN * TBK * 2;
+// CTAS = 2: a CTA pair (cta_group::2) computes one 256 x BN tile; each CTA holds 128 rows of A and BN/2 columns of B,
+// so per MMA cycle only half of B crosses each SM's shared memory (the 1-CTA kernel is shared-memory-bandwidth bound).
+template <int BN, int CTAS = 1> struct TcCfg {
+  static constexpr int kBBytes = (BN / CTAS) * TBK * 2;
   static constexpr int kStageBytes = A_TILE_BYTES + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (kStageBytes >= 49152) ? 4 : (kStageBytes >= 32768 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kScratchOff = kStages * kStageBytes + 256 /* barriers */;
   static constexpr int kSmemBytes = kScratchOff + (TC_EPI_THREADS / 32) * 2048 /* epilogue scratch */ + 1024 /* align slack */;
@@ -279,21 +281,25 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpilogue& e, uint8_t* 
 struct TcUnit {
   int m0, n0, kb0, kb1;
 };
-__device__ __forceinline__ TcUnit tc_unit(int u, int num_m, int num_kb, int splits, int BN) {
+__device__ __forceinline__ TcUnit tc_unit(int u, int num_m, int num_kb, int splits, int BN, int tile_rows = TBM) {
   const int tile = u / splits;
   const int sp = u - tile * splits;
   TcUnit w;
-  w.m0 = (tile % num_m) * TBM;
+  w.m0 = (tile % num_m) * tile_rows;
   w.n0 = (tile / num_m) * BN;
   w.kb0 = (int)(((int64_t)sp * num_kb) / splits);
   w.kb1 = (int)(((int64_t)(sp + 1) * num_kb) / splits);
   return w;
 }
 
-template <int BN, typename TC, int VARIANT>
+template <int BN, typename TC, int VARIANT, int CTAS>
 __device__ __forceinline__ void tc_epilogue_loop(const TcEpilogue& epi, uint32_t tmem_base, uint64_t* tmem_full,
                                                  uint64_t* tmem_empty, uint8_t* scratch, int M, int N, int num_m,
                                                  int num_kb, int num_units, int warp, int lane) {
+  const int cta_rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+  const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
+  // the MMA issuer (leader CTA) waits for the accumulator to be drained by the epilogue warps of BOTH CTAs
+  const uint32_t empty_addr0 = CTAS == 2 ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0;
   constexpr int COLS = BN / 4;                    // columns per epilogue warp
   constexpr int CW = COLS < 32 ? COLS : 32;       // columns per tcgen05.ld
   const int e = warp - 4;
@@ -302,11 +308,11 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcEpilogue& epi, uint32_t
   uint8_t* scr = scratch + e * TC_SCR_BYTES;
   int acc = 0;
   uint32_t acc_ph = 0;
-  for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-    const TcUnit w = tc_unit(u, num_m, num_kb, epi.splits, BN);
+  for (int u = unit0; u < num_units; u += unit_step) {
+    const TcUnit w = tc_unit(u, num_m, num_kb, epi.splits, BN, TBM * CTAS);
     mbar_wait(&tmem_full[acc], acc_ph);
     tc_fence_after();
-    const int m0w = w.m0 + wq * 32;               // first row of this warp's 32-row slab
+    const int m0w = w.m0 + cta_rank * TBM + wq * 32;   // first row of this warp's 32-row slab
     const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + cg * COLS);
 #pragma unroll
     for (int c = 0; c < COLS / CW; ++c) {
@@ -318,19 +324,24 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcEpilogue& epi, uint32_t
       if (m0w < M && nc < N) tc_epilogue_chunk<TC, VARIANT, CW>(epi, scr, lane, m0w, M, nc, N, r);
     }
     tc_fence_before();
-    mbar_arrive(&tmem_empty[acc]);
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (CTAS == 2) mbar_arrive_cluster(empty_addr0 + (uint32_t)(acc * 8));
+      else mbar_arrive(&tmem_empty[acc]);
+    }
     acc ^= 1;
     if (acc == 0) acc_ph ^= 1u;
   }
 }
 
 // VMASK: bit i set → TcVariant i has a specialised epilogue in this instantiation (others use the generic one).
-template <int BN, bool A_MN, bool B_MN, typename TC, unsigned VMASK>
+template <int BN, bool A_MN, bool B_MN, typename TC, unsigned VMASK, int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, TcEpilogue epi) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, CTAS>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int BNL = BN / CTAS;                 // B columns held (and loaded) by this CTA
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);   // 1024 B alignment for SW128
@@ -343,6 +354,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmA);
@@ -353,61 +365,88 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], TC_EPI_THREADS);
+      mbar_init(&tmem_empty[a], CTAS * (TC_EPI_THREADS / 32));     // one arrival per epilogue warp (of each CTA)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_m = (M + TBM - 1) / TBM;
+  const int num_m = (M + TBM * CTAS - 1) / (TBM * CTAS);
   const int num_n = (N + BN - 1) / BN;
   const int num_kb = (K + TBK - 1) / TBK;
   const int num_units = num_m * num_n * epi.splits;
+  const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A rows and its own slice of B) =====================
     int s = 0;
     uint32_t ph = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-      const TcUnit w = tc_unit(u, num_m, num_kb, epi.splits, BN);
+    for (int u = unit0; u < num_units; u += unit_step) {
+      const TcUnit w = tc_unit(u, num_m, num_kb, epi.splits, BN, TBM * CTAS);
+      const int m0 = w.m0 + cta_rank * TBM;
+      const int n0 = w.n0 + cta_rank * BNL;
       for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
         uint8_t* a_dst = smem + s * Cfg::kStageBytes;
         uint8_t* b_dst = a_dst + A_TILE_BYTES;
         const int k0 = kb * TBK;
-        if constexpr (!A_MN) {
-          tma_load_2d(a_dst, &tmA, &full_bar[s], k0, w.m0);
-        } else {
+        if constexpr (CTAS == 2) {
+          // both CTAs' bytes are counted on the LEADER's barrier (the MMA issuer lives there)
+          const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d_pair(a_dst, &tmA, bar, k0, m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < TBM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full_bar[s], w.m0 + 64 * j, k0);
-        }
-        if constexpr (!B_MN) {
-          tma_load_2d(b_dst, &tmB, &full_bar[s], k0, w.n0);
-        } else {
+            for (int j = 0; j < TBM / 64; ++j) tma_load_2d_pair(a_dst + j * 8192, &tmA, bar, m0 + 64 * j, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_pair(b_dst, &tmB, bar, k0, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], w.n0 + 64 * j, k0);
+            for (int j = 0; j < BNL / 64; ++j) tma_load_2d_pair(b_dst + j * 8192, &tmB, bar, n0 + 64 * j, k0);
+          }
+        } else {
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d(a_dst, &tmA, &full_bar[s], k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < TBM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full_bar[s], m0 + 64 * j, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(b_dst, &tmB, &full_bar[s], k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BNL / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + 64 * j, k0);
+          }
         }
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(TBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+    // ===================== MMA issuer (the leader CTA issues for the pair) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(TBM * CTAS, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int s = 0;
     uint32_t ph = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-      const TcUnit w = tc_unit(u, num_m, num_kb, epi.splits, BN);
-      mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
+    for (int u = unit0; u < num_units; u += unit_step) {
+      const TcUnit w = tc_unit(u, num_m, num_kb, epi.splits, BN, TBM * CTAS);
+      if constexpr (CTAS == 2) mbar_wait_cluster(&tmem_empty[acc], acc_ph ^ 1u);
+      else mbar_wait(&tmem_empty[acc], acc_ph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int kb = w.kb0; kb < w.kb1; ++kb) {
@@ -423,20 +462,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                    : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
           const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
                                    : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_f16_ss(d_tmem, da, db, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
+          if constexpr (CTAS == 2) umma_f16_ss_pair(d_tmem, da, db, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
+          else umma_f16_ss(d_tmem, da, db, idesc, (kb != w.kb0 || k != 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);            // frees the smem slot once these MMAs retire
+        // frees the smem slot (in both CTAs) once these MMAs retire
+        if constexpr (CTAS == 2) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
-      umma_commit(&tmem_full[acc]);            // accumulator complete → epilogue
+      // accumulator complete → epilogue warps (of both CTAs)
+      if constexpr (CTAS == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1u;
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
 #define VG_TC_EPI(V)                                                                                               \
-  tc_epilogue_loop<BN, TC, V>(epi, tmem_base, tmem_full, tmem_empty, smem + Cfg::kScratchOff, M, N, num_m, num_kb, \
-                              num_units, warp, lane)
+  tc_epilogue_loop<BN, TC, V, CTAS>(epi, tmem_base, tmem_full, tmem_empty, smem + Cfg::kScratchOff, M, N, num_m,    \
+                                    num_kb, num_units, warp, lane)
     const int var = epi.variant;
     bool done = false;
     if constexpr ((VMASK >> TCV_PLAIN) & 1u) { if (!done && var == TCV_PLAIN) { VG_TC_EPI(TCV_PLAIN); done = true; } }
@@ -452,15 +494,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if constexpr (CTAS == 2) {
+    cluster_sync_all();          // the peer may still multicast commits into / read from this CTA's shared memory
+    if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
-template <int BN, bool A_MN, bool B_MN, typename TC, unsigned VMASK>
+template <int BN, bool A_MN, bool B_MN, typename TC, unsigned VMASK, int CTAS>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a, TcEpilogue epi,
                      cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TC, VMASK>;
+  using Cfg = TcCfg<BN, CTAS>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, TC, VMASK, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     VG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -468,24 +515,33 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_ge
   }
   // a variant this instantiation does not specialise falls back to the generic epilogue (TCV_RED has no generic
   // equivalent: the host only selects it where VMASK carries it)
-  const int64_t units = ceil_div(a->M, TBM) * ceil_div(a->N, BN) * epi.splits;
-  const int grid = (int)(units < kNumSMs ? units : kNumSMs);
-  kern<<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(tmA, tmB, (int)a->M, (int)a->N, (int)a->K, epi);
-  VG_LAUNCH_CHECK("vg_gemm(tcgen05)");
+  const int64_t units = ceil_div(a->M, TBM * CTAS) * ceil_div(a->N, BN) * epi.splits;
+  const int max_groups = kNumSMs / CTAS;
+  const int grid = (int)(units < max_groups ? units : max_groups) * CTAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CTAS == 2 ? 1 : 0;
+  VG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, (int)a->M, (int)a->N, (int)a->K, epi));
   return 0;
 }
 
-template <bool A_MN, bool B_MN, unsigned VMASK>
+// bn: 64 / 128 / 256 (one CTA per tile) or 512 = a CTA pair on 256 x 256 tiles
+template <bool A_MN, bool B_MN, unsigned VMASK, typename TC>
 static int launch_tc_layout(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
                             const TcEpilogue& epi, cudaStream_t st) {
-  if (a->c_dtype == VG_BF16) {
-    if (bn == 256) return launch_tc<256, A_MN, B_MN, __nv_bfloat16, VMASK>(tmA, tmB, a, epi, st);
-    if (bn == 128) return launch_tc<128, A_MN, B_MN, __nv_bfloat16, VMASK>(tmA, tmB, a, epi, st);
-    return launch_tc<64, A_MN, B_MN, __nv_bfloat16, VMASK>(tmA, tmB, a, epi, st);
-  }
-  if (bn == 256) return launch_tc<256, A_MN, B_MN, float, VMASK>(tmA, tmB, a, epi, st);
-  if (bn == 128) return launch_tc<128, A_MN, B_MN, float, VMASK>(tmA, tmB, a, epi, st);
-  return launch_tc<64, A_MN, B_MN, float, VMASK>(tmA, tmB, a, epi, st);
+  if (bn == 512) return launch_tc<256, A_MN, B_MN, TC, VMASK, 2>(tmA, tmB, a, epi, st);
+  if (bn == 256) return launch_tc<256, A_MN, B_MN, TC, VMASK, 1>(tmA, tmB, a, epi, st);
+  if (bn == 128) return launch_tc<128, A_MN, B_MN, TC, VMASK, 1>(tmA, tmB, a, epi, st);
+  return launch_tc<64, A_MN, B_MN, TC, VMASK, 1>(tmA, tmB, a, epi, st);
 }
 
 // specialised-variant masks per operand layout (what the model launches: forward = K/K with activations,
@@ -495,13 +551,21 @@ constexpr unsigned TCM_KMN = (1u << TCV_PLAIN) | (1u << TCV_MULT) | (1u << TCV_R
 constexpr unsigned TCM_MNK = (1u << TCV_RED);
 constexpr unsigned TCM_MNMN = (1u << TCV_PLAIN) | (1u << TCV_RED);
 
-int gemm_tc_launch_kk(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
-                      const TcEpilogue& epi, cudaStream_t st);
-int gemm_tc_launch_kmn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
-                       const TcEpilogue& epi, cudaStream_t st);
-int gemm_tc_launch_mnk(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
-                       const TcEpilogue& epi, cudaStream_t st);
-int gemm_tc_launch_mnmn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
-                        const TcEpilogue& epi, cudaStream_t st);
+int gemm_tc_launch_kk_bf16(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
+                              const TcEpilogue& epi, cudaStream_t st);
+int gemm_tc_launch_kk_f32(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
+                              const TcEpilogue& epi, cudaStream_t st);
+int gemm_tc_launch_kmn_bf16(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
+                              const TcEpilogue& epi, cudaStream_t st);
+int gemm_tc_launch_kmn_f32(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
+                              const TcEpilogue& epi, cudaStream_t st);
+int gemm_tc_launch_mnk_bf16(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
+                              const TcEpilogue& epi, cudaStream_t st);
+int gemm_tc_launch_mnk_f32(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
+                              const TcEpilogue& epi, cudaStream_t st);
+int gemm_tc_launch_mnmn_bf16(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
+                              const TcEpilogue& epi, cudaStream_t st);
+int gemm_tc_launch_mnmn_f32(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
+                              const TcEpilogue& epi, cudaStream_t st);
 
 }  // namespace vg

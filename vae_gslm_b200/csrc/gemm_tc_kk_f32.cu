@@ -1,0 +1,9 @@
+// gemm_tc_kk_f32.cu — tcgen05 GEMM instantiations: A K-major, B K-major, f32 C (see gemm_tc_kernel.cuh).
+#include "gemm_tc_kernel.cuh"
+
+namespace vg {
+int gemm_tc_launch_kk_f32(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
+                              const TcEpilogue& epi, cudaStream_t st) {
+  return launch_tc_layout<false, false, TCM_KK, float>(bn, tmA, tmB, a, epi, st);
+}
+}  // namespace vg

@@ -1,0 +1,9 @@
+// gemm_tc_kmn_bf16.cu — tcgen05 GEMM instantiations: A K-major, B MN-major, bf16 C (see gemm_tc_kernel.cuh).
+#include "gemm_tc_kernel.cuh"
+
+namespace vg {
+int gemm_tc_launch_kmn_bf16(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_gemm_args* a,
+                              const TcEpilogue& epi, cudaStream_t st) {
+  return launch_tc_layout<false, true, TCM_KMN, __nv_bfloat16>(bn, tmA, tmB, a, epi, st);
+}
+}  // namespace vg

@@ -10,7 +10,7 @@
 
 namespace vg {
 
-constexpr int kRmsWarps = 4;          // warps (= rows in flight) per CTA
+constexpr int kRmsWarps = 8;          // warps (= rows in flight) per CTA
 constexpr int kRmsMaxIters = 8;       // register-resident path: dim <= 8*256 = 2048
 
 template <typename TX, typename TY, int ITERS>
@@ -53,7 +53,7 @@ rmsnorm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ scale,
 }
 
 template <typename TX, typename TG, int ITERS>
-__global__ void __launch_bounds__(kRmsWarps * 32)
+__global__ void __launch_bounds__(kRmsWarps * 32, 2)
 rmsnorm_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ scale,
                    const float* __restrict__ rstd, const uint8_t* __restrict__ mask,
                    const TX* __restrict__ dres, TX* __restrict__ dx, float* __restrict__ partial,
@@ -150,7 +150,7 @@ colsum_partials_kernel(const float* __restrict__ partial, float* __restrict__ ou
 
 static int rms_bwd_blocks(int64_t rows) {
   int64_t want = ceil_div(rows, kRmsWarps);
-  int64_t cap = (int64_t)kNumSMs * 4;      // 16 warps per SM: enough rows in flight to cover HBM latency
+  int64_t cap = (int64_t)kNumSMs * 2;      // 2 CTAs x 8 warps per SM: 16 rows in flight per SM cover HBM latency
   return (int)(want < cap ? want : cap);
 }
 

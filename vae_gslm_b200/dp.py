@@ -37,12 +37,10 @@ class GradReducer:
         self.is_cuda = self.buckets[0][0].is_cuda
         self.comm_stream = torch.cuda.Stream() if self.is_cuda else None
         self._launched: List[bool] = []
-        direct = {id(p) for p in arena.direct}
         for _, members in self.buckets:
-            for p in members:
-                if id(p) not in direct:       # autograd-accumulated gradients announce themselves through a hook
-                    p.register_post_accumulate_grad_hook(self._hook)
-        arena.on_grad_ready = self._ready     # direct-wgrad parameters are announced by ops._wgrad
+            for p in members:                 # autograd-accumulated gradients announce themselves through a hook;
+                p.register_post_accumulate_grad_hook(self._hook)
+        arena.on_grad_ready = self._ready     # gradients written directly by ops._wgrad/_bgrad/_RMSNorm call this
 
     # ------------------------------------------------------------------ per-backward protocol
     def prepare(self, last_micro_batch: bool = True) -> None:
