@@ -150,6 +150,38 @@ int vg_kv_append(const void* k, const void* v, int64_t ld, void* k_cache, void* 
                  int64_t B, int64_t H, int64_t D, int64_t T, int64_t Tmax, int64_t pos, int dtype,
                  vg_stream_t stream);
 
+/* ---- weight-streaming linear layer for the cached generation step (decode batch B <= 256 rows):
+ * every nn.Linear that LVTR.step runs on ONE new frame per sequence — attention.py:52,79, transformer/layers.py:82,152,
+ * lvtr.py:171,172,194,195 — with the RMSNorm in front of it (norm.py:28-32) folded in.
+ *   v[b,n] = sum_k (x[b,k] * norm_scale[k]) * W[n,k]            (norm_scale nullable: plain x)
+ *   v     *= rsqrt(x_ss[b] / K + norm_eps)                       (only with norm_scale; x_ss[b] = sum_k x[b,k]^2)
+ *   v      = act(v + bias[n]) + residual[b,n]                    (bias, residual nullable; act: none/ReLU/GELU/SiLU)
+ *   y[b,n] = bf16(v)  and/or  y_f32[b,n] = v
+ *   y_ss[b] += sum_n bf16(v)^2                                   (nullable; feeds the next layer's x_ss — the caller
+ *                                                                 zeroes it, or passes it as `zero_ss` to an EARLIER
+ *                                                                 call that does not read it)
+ * Each SM streams a disjoint slab of W once (cp.async, issued before the programmatic-dependent-launch wait so that
+ * it overlaps the previous kernel when allow_overlap = 1).  `workspace` (vg_decode_linear_workspace bytes) must be
+ * ZERO-FILLED once by the caller; the kernel leaves it zeroed.  x / W are bf16; K % 64 == 0; ldx, ldw % 8 == 0.   */
+typedef struct {
+  int64_t B, N, K;
+  const void* x; int64_t ldx;
+  const void* W; int64_t ldw;
+  const float* norm_scale; const float* x_ss; float norm_eps;
+  const float* bias;
+  int32_t act;
+  const void* residual; int64_t ld_res;   /* may alias y (in-place residual update) */
+  void* y; int64_t ldy;
+  float* y_f32; int64_t ldy_f32;
+  float* y_ss;
+  float* zero_ss;                          /* nullable: [B] floats cleared by this call (after its dependency wait) */
+  int32_t allow_overlap;                   /* 1: launch with programmatic stream serialization (PDL) */
+} vg_decode_linear_args;
+size_t vg_decode_linear_workspace(int64_t max_batch, int64_t max_n);
+int    vg_decode_linear(const vg_decode_linear_args* a, void* workspace, size_t workspace_bytes, vg_stream_t stream);
+/* debug aid: when non-null, CTA 0 of every following vg_decode_linear launch writes 7 clock64 phase stamps to buf */
+int    vg_debug_decode_linear_trace(void* buf /* device, 32 x uint64, nullable */);
+
 /* ---- fused latent front end: lvtr.py:151-169 (+ linear/layers.py:87-134,150-152, lvtr.py:390-392)
  * per frame: mean/logstd heads (Linear L→L), z = (mean + exp(logstd)·eps·temperature)·mask,
  * log_q = (−logstd − 0.5 − 0.5 ln 2π)·mask, u = tok_emb[id]·mask + ReLU(Wf z + bf),

@@ -145,6 +145,44 @@ def test_gemm_tcgen05_split_k(M, N, K):
     assert rel_err(acc, ref2) < 2e-3
 
 
+# ------------------------------------------------------------------------------------ decode (skinny) linear
+@pytest.mark.parametrize("B", [1, 5, 16, 64, 100, 256])
+@pytest.mark.parametrize("N,K", [(3072, 1024), (1024, 4096), (520, 1024), (50, 128), (1024, 64)])
+def test_decode_linear(B, N, K):
+    """vg_decode_linear against torch: plain, and with the folded RMSNorm + bias + GELU + residual + Σy² epilogue;
+    the self-resetting workspace must stay zero so that back-to-back calls are independent."""
+    bf = torch.bfloat16
+    x = torch.randn(B, K, device=DEV).to(bf)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(bf)
+    ws = ops.decode_linear_workspace(B, N, DEV)
+    out = torch.empty(B, N, device=DEV, dtype=bf)
+    for _ in range(2):
+        ops.decode_linear(x, w, ws, out=out)
+        assert rel_err(out, x.float() @ w.float().t()) < 1e-2
+    assert int(ws.count_nonzero()) == 0
+    scale = 1.0 + 0.1 * torch.randn(K, device=DEV)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(B, N, device=DEV).to(bf)
+    x_ss = (x.float() ** 2).sum(-1)
+    y_ss = torch.zeros(B, device=DEV)
+    zero_me = torch.ones(B, device=DEV)
+    out32 = torch.empty(B, N, device=DEV)
+    ops.decode_linear(x, w, ws, norm_scale=scale, x_ss=x_ss, norm_eps=1e-6, bias=bias, act=ops.ACT_GELU, residual=res,
+                      out=out, out_f32=out32, y_ss=y_ss, zero_ss=zero_me)
+    rstd = torch.rsqrt(x_ss / K + 1e-6)
+    xn = (x.float() * scale.to(bf).float()).to(bf).float()
+    ref = torch.nn.functional.gelu((xn @ w.float().t()) * rstd[:, None] + bias) + res.float()
+    assert rel_err(out32, ref) < 1e-2 and rel_err(out, ref) < 1.5e-2
+    assert rel_err(y_ss, (out.float() ** 2).sum(-1)) < 1e-3
+    assert float(zero_me.abs().max()) == 0.0 and int(ws.count_nonzero()) == 0
+    # strided input view + in-place residual update (how the engine chains out_proj / linear2)
+    wide = torch.randn(B, 2 * K, device=DEV).to(bf)
+    xr = torch.randn(B, N, device=DEV).to(bf)
+    ref2 = wide[:, K:].float() @ w.float().t() + xr.float()
+    ops.decode_linear(wide[:, K:], w, ws, residual=xr, out=xr, overlap=False)
+    assert rel_err(xr, ref2) < 1.5e-2
+
+
 def test_colsum():
     x = torch.randn(1000, 520, device=DEV)
     assert rel_err(ops.colsum(x), x.sum(0)) < 1e-5

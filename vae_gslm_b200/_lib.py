@@ -45,6 +45,23 @@ class GemmArgs(C.Structure):
     ]
 
 
+class DecodeLinearArgs(C.Structure):
+    _fields_ = [
+        ("B", _i64), ("N", _i64), ("K", _i64),
+        ("x", _p), ("ldx", _i64),
+        ("W", _p), ("ldw", _i64),
+        ("norm_scale", _p), ("x_ss", _p), ("norm_eps", _f32),
+        ("bias", _p),
+        ("act", _i32),
+        ("residual", _p), ("ld_res", _i64),
+        ("y", _p), ("ldy", _i64),
+        ("y_f32", _p), ("ldy_f32", _i64),
+        ("y_ss", _p),
+        ("zero_ss", _p),
+        ("allow_overlap", _i32),
+    ]
+
+
 class LatentFrontArgs(C.Structure):
     _fields_ = [
         ("B", _i64), ("T", _i64),
@@ -114,6 +131,9 @@ _SIGNATURES = {
     "vg_attn_decode": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _f32, C.c_int,
                                  _p, _sz, _p]),
     "vg_add_i32": (C.c_int, [_p, _i32, _p]),
+    "vg_decode_linear_workspace": (_sz, [_i64, _i64]),
+    "vg_decode_linear": (C.c_int, [C.POINTER(DecodeLinearArgs), _p, _sz, _p]),
+    "vg_debug_decode_linear_trace": (C.c_int, [_p]),
     "vg_kv_append": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, C.c_int, _p]),
     "vg_latent_front_fwd": (C.c_int, [C.POINTER(LatentFrontArgs), _p]),
     "vg_latent_front_bwd_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),

@@ -21,6 +21,9 @@ attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __rest
                    T* __restrict__ out, float* __restrict__ partial, const float* __restrict__ slopes,
                    int H, int Tmax, int pos_arg, const int32_t* __restrict__ pos_dev, int splits, float scale) {
   __shared__ float sm_m[DEC_GROUPS], sm_l[DEC_GROUPS];
+  // programmatic dependent launch: the weight-streaming GEMM that follows (decode_linear.cu) may start prefetching its
+  // weight slab now; it still waits (griddepcontrol.wait) for this grid to finish before it reads our output
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int pos = pos_dev ? min(*pos_dev, Tmax - 1) : pos_arg;   // device-resident position for graph replay
   __shared__ float sm_o[DEC_GROUPS][DD];
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -114,6 +117,7 @@ attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __rest
 
 template <typename T>
 __global__ void attn_decode_merge_kernel(const float* __restrict__ partial, T* __restrict__ out, int H, int splits) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // see attn_decode_kernel
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
   const float* pp = partial + ((int64_t)b * H + h) * splits * (DD + 2);
   float M = -CUDART_INF_F;

@@ -94,6 +94,10 @@ class LVTR(nn.Module):
                 TimeAggregation())
         self.use_tokens = self.tokens is not None
         self.compute_dtype = torch.float32
+        self.use_decode_engine = True       # bf16 single-frame steps run on decode.DecodeEngine ...
+        # ... up to this batch: measured on B200 (profiles/r01_decode.md) the weight-streaming engine wins below ~48
+        # sequences (0.57 vs 1.21 ms per step at B=1), the tcgen05 layer-by-layer path above (2.0 vs 3.7 ms at B=256)
+        self.decode_engine_max_batch = 48
 
     # ------------------------------------------------------------------ configuration
     def set_compute_dtype(self, dtype: torch.dtype) -> "LVTR":
@@ -245,15 +249,23 @@ class LVTR(nn.Module):
             s0 = self.initial_state(x.shape[0], x.device) if init_state is None else init_state
             u = torch.cat([s0.reshape(x.shape[0], 1, -1).to(u.dtype), u], 1)
         stack = self.transformer[0]
-        z_given = stack.run(TensorMask(u), memory=c, past_kv=past_kv, return_attn=return_attn, return_kv=True)
-        outputs = {"transformer_latent": z_given["output"], "kv": z_given["kv"]}
-        if return_distrbution:
-            outputs["z_given"] = z_given
-        if return_attn:
-            outputs["self_attn"] = z_given["self_attn"]
-        H = z_given["output"].value
+        engine = self._decode_engine(u, past_kv, c, return_attn, return_distrbution)
+        if engine is not None:
+            # single new frame per sequence, bf16: the weight-streaming decode engine (decode.py), 5 kernels per layer
+            H2, head2, logits2 = engine.run(u[:, 0], past_kv)
+            H = H2.view(u.shape[0], 1, -1)
+            head, logits = head2.view(u.shape[0], 1, -1), logits2.view(u.shape[0], 1, -1)
+            outputs = {"transformer_latent": TensorMask(H), "kv": past_kv}
+        else:
+            z_given = stack.run(TensorMask(u), memory=c, past_kv=past_kv, return_attn=return_attn, return_kv=True)
+            outputs = {"transformer_latent": z_given["output"], "kv": z_given["kv"]}
+            if return_distrbution:
+                outputs["z_given"] = z_given
+            if return_attn:
+                outputs["self_attn"] = z_given["self_attn"]
+            H = z_given["output"].value
+            c_lat, head, logits = self._post_stack(H)
         Bq, Tq, _ = H.shape
-        c_lat, head, logits = self._post_stack(H)
         Ld = self.hp.latent_dim
         if eps is None:
             eps = torch.randn(Bq, Tq, Ld, device=H.device)
@@ -272,6 +284,23 @@ class LVTR(nn.Module):
         if return_logits:
             outputs["logits"] = logits
         return outputs
+
+    def _decode_engine(self, u: torch.Tensor, past_kv, c, return_attn: bool, return_distribution: bool):
+        """the DecodeEngine for this batch size when the call is a plain single-frame cached bf16 step, else None."""
+        from ...modules.attention.kvcache import LayerKV
+        if (not self.use_decode_engine or u.shape[1] != 1 or c is not None or return_attn or return_distribution
+                or past_kv is None or not isinstance(past_kv[0], LayerKV) or not u.is_cuda
+                or self.compute_dtype != torch.bfloat16 or u.shape[0] > self.decode_engine_max_batch):
+            return None
+        from ...decode import DecodeEngine
+        engines = self.__dict__.setdefault("_decode_engines", {})
+        stack = self.transformer[0]
+        stamp = tuple(p._version for p in stack.parameters())     # rebuilt when the weights have been updated
+        ent = engines.get(u.shape[0])
+        if ent is None or ent[0] != stamp:
+            ent = (stamp, DecodeEngine(self, u.shape[0], u.device))
+            engines[u.shape[0]] = ent
+        return ent[1]
 
     # ------------------------------------------------------------------ auxiliary entry points
     @torch.no_grad()

@@ -517,7 +517,8 @@ def kv_append(k: torch.Tensor, v: torch.Tensor, k_cache: torch.Tensor, v_cache: 
 @torch.no_grad()
 def attention_decode(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, pos: int,
                      slopes: Optional[torch.Tensor], pos_dev: Optional[torch.Tensor] = None,
-                     scale: Optional[float] = None, splits: Optional[int] = None) -> torch.Tensor:
+                     scale: Optional[float] = None, splits: Optional[int] = None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """single-token step: append this token's k/v at ``pos`` and attend over cache rows [0, pos]."""
     B, C3 = qkv.shape
     _, H, Tmax, D = k_cache.shape
@@ -526,7 +527,9 @@ def attention_decode(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Te
         # (CUDA-graph replay) the split count is frozen at capture time, so size it for the whole cache
         horizon = Tmax if pos_dev is not None else pos + 1
         splits = max(1, min(16, (2 * 148 + B * H - 1) // (B * H), (horizon + 63) // 64))
-    out = torch.empty((B, C3 // 3), dtype=qkv.dtype, device=qkv.device)
+    if out is None:
+        out = torch.empty((B, C3 // 3), dtype=qkv.dtype, device=qkv.device)
+    assert out.shape == (B, C3 // 3) and out.is_contiguous() and out.dtype == qkv.dtype
     ws = L.workspace(L.load().vg_attn_decode_workspace(B, H, D, splits), qkv.device)
     L.call("vg_attn_decode", L.ptr(qkv), L.ptr(k_cache), L.ptr(v_cache), L.ptr(out), L.ptr(slopes), B, H, D, Tmax,
            pos, L.ptr(pos_dev), splits, float(scale), L.dtype_id(qkv.dtype), L.ptr(ws), ws.numel(), L.stream())
@@ -795,3 +798,42 @@ def sample_token(logits: torch.Tensor, u: Optional[torch.Tensor], temperature: f
     L.call("vg_sample_token", L.ptr(lg), lg.stride(0), L.ptr(uu), float(temperature), L.ptr(out), rows, vocab,
            L.dtype_id(lg.dtype), L.stream())
     return out.view(logits.shape[:-1])
+
+
+# ------------------------------------------------------------------------------- decode (skinny) linear
+def decode_linear(x: torch.Tensor, w: torch.Tensor, ws: torch.Tensor, *, norm_scale: Optional[torch.Tensor] = None,
+                  x_ss: Optional[torch.Tensor] = None, norm_eps: float = 0.0, bias: Optional[torch.Tensor] = None,
+                  act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                  out_f32: Optional[torch.Tensor] = None, y_ss: Optional[torch.Tensor] = None,
+                  zero_ss: Optional[torch.Tensor] = None, overlap: bool = True) -> None:
+    """Weight-streaming linear for the cached generation step (vg_decode_linear): x [B,K] bf16 (row stride free),
+    w [N,K] bf16, ``ws`` a zero-filled workspace of ``decode_linear_workspace`` bytes (left zeroed)."""
+    B, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.stride(1) == 1 and w.stride(1) == 1
+    a = L.DecodeLinearArgs()
+    a.B, a.N, a.K = B, N, K
+    a.x, a.ldx, a.W, a.ldw = L.ptr(x), x.stride(0), L.ptr(w), w.stride(0)
+    if norm_scale is not None:
+        assert norm_scale.dtype == torch.float32 and x_ss is not None and x_ss.dtype == torch.float32
+        a.norm_scale, a.x_ss, a.norm_eps = L.ptr(norm_scale), L.ptr(x_ss), float(norm_eps)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+        a.bias = L.ptr(bias)
+    a.act = act
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == (B, N) and residual.stride(1) == 1
+        a.residual, a.ld_res = L.ptr(residual), residual.stride(0)
+    if out is not None:
+        assert out.dtype == torch.bfloat16 and out.shape == (B, N) and out.stride(1) == 1
+        a.y, a.ldy = L.ptr(out), out.stride(0)
+    if out_f32 is not None:
+        assert out_f32.dtype == torch.float32 and out_f32.shape == (B, N) and out_f32.stride(1) == 1
+        a.y_f32, a.ldy_f32 = L.ptr(out_f32), out_f32.stride(0)
+    a.y_ss, a.zero_ss = L.ptr(y_ss), L.ptr(zero_ss)
+    a.allow_overlap = int(overlap)
+    L.call("vg_decode_linear", C.byref(a), L.ptr(ws), ws.numel(), L.stream())
+
+
+def decode_linear_workspace(max_batch: int, max_n: int, device) -> torch.Tensor:
+    return torch.zeros(int(L.load().vg_decode_linear_workspace(max_batch, max_n)), dtype=torch.uint8, device=device)
