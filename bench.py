@@ -201,7 +201,10 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all instances of one step)",
                 "achieved": round(achieved, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["bf16_sustained"], 4), "peak_source": peaks["src"] + " sustained",
-                "traffic": None, "launches_per_step": len(prof), "gemm_ms_per_step": round(gemm_ms, 3),
+                # DRAM read+write bytes of ONE representative launch (FFN1 forward, bias+GELU+saved derivative, 8000x4096x1024)
+                # from `ncu --set full`: profiles/r01_gemm_gelu_pair_ncu.md (algorithmic bytes of that launch: 155.8e6)
+                "traffic": 112.9e6, "traffic_launch": "ffn1 fwd 8000x4096x1024 (ncu --set full, profiles/r01_gemm_gelu_pair_ncu.md)",
+                "launches_per_step": len(prof), "gemm_ms_per_step": round(gemm_ms, 3),
                 "share_of_step": round(gemm_ms / step_ms, 3)}
 
     result = {
@@ -240,7 +243,7 @@ def run_ours(args):
         os._exit(0)
 
 
-def decode_bench(model, dev, peaks, batches=(1, 64), prompt=150, steps=48):
+def decode_bench(model, dev, peaks, batches=(1, 64, 256), prompt=150, steps=48):
     """cached generation (configs[2]): 3 s prompt, prefill then `steps` single-token steps; frames/s and the HBM
     roofline of SURVEY §8d: bytes(B,Tk) = 408.7 MB weights + B·65,536·(Tk+1)."""
     from vae_gslm_b200.utils.tensormask import TensorMask
@@ -272,7 +275,10 @@ def decode_bench(model, dev, peaks, batches=(1, 64), prompt=150, steps=48):
         roof = B * peaks["hbm_gbs"] * 1e9 / bytes_step
         out[f"B{B}"] = {"frames_per_sec": round(B / (ms / 1e3), 1), "ms_per_step": round(ms, 3),
                         "hbm_roofline_frames_per_sec": round(roof, 1), "frac": round(B / (ms / 1e3) / roof, 4),
-                        "mean_tk": tk, "mode": "single-token step replayed from a CUDA graph"}
+                        "mean_tk": tk, "mode": "single-token step replayed from a CUDA graph",
+                        "path": "decode engine (vg_decode_linear)" if (model.use_decode_engine and
+                                                                       B <= model.decode_engine_max_batch)
+                        else "layer-by-layer (tcgen05 GEMM)"}
     return out
 
 
