@@ -161,8 +161,65 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int j0 = j * TK;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row maximum of the biased, masked scores (log2 domain)
+      // Tiles entirely below the diagonal and inside kv_len need no mask: the bias is an affine function of the
+      // column, so scores are formed two at a time with packed f32x2 FMAs (the softmax warps are issue-bound: the
+      // tensor pipe needs ~512 cycles per key tile, the scalar loops below ~3000).
+      const bool full_tile = (j0 + TK - 1 <= sh.q_offset + q0) && (j0 + TK <= klen);      // CTA-uniform
       float mx = -CUDART_INF_F;
+      float rsum = 0.f;
+      float m_new, m_use, corr;
+      if (full_tile) {
+        const float rowc = -slope2 * (float)ia;
+        const f32x2_t sc2 = splat2(scale2), sl2 = splat2(slope2);
+#pragma unroll 1
+        for (int c = 0; c < TK / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + lane_addr + c * 32, v);
+          tmem_ld_wait();
+          const f32x2_t cb0 = splat2(fmaf(slope2, (float)(j0 + c * 32), rowc));
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const f32x2_t cb = fma2(sl2, pack2((float)e, (float)(e + 1)), cb0);
+            float a, b;
+            unpack2(fma2(pack2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sc2, cb), a, b);
+            mx = fmaxf(mx, fmaxf(a, b));
+          }
+        }
+        m_new = fmaxf(m, mx);
+        m_use = m_new;                                       // finite: every key of the tile is visible
+        corr = ex2_approx(m - m_use);
+        f32x2_t rs2 = splat2(0.f);
+#pragma unroll 1
+        for (int c = 0; c < TK / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + lane_addr + c * 32, v);
+          tmem_ld_wait();
+          const f32x2_t cb0 = splat2(fmaf(slope2, (float)(j0 + c * 32), rowc) - m_use);
+          float p[32];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const f32x2_t cb = fma2(sl2, pack2((float)e, (float)(e + 1)), cb0);
+            float a, b;
+            unpack2(fma2(pack2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sc2, cb), a, b);
+            p[e] = ex2_approx(a);
+            p[e + 1] = ex2_approx(b);
+            rs2 = add2(rs2, pack2(p[e], p[e + 1]));
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 pk;
+            pk.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
+            pk.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+            pk.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
+            pk.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(sP + sw128_piece(r, c * 4 + g)) = pk;
+          }
+        }
+        float ra, rb;
+        unpack2(rs2, ra, rb);
+        rsum = ra + rb;
+      } else {
+      // pass 1: row maximum of the biased, masked scores (log2 domain)
 #pragma unroll 1
       for (int c = 0; c < TK / 32; ++c) {
         uint32_t v[32];
@@ -175,10 +232,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mx = fmaxf(mx, (ja <= ia && ja < klen) ? s2 : -CUDART_INF_F);
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-      const float corr = ex2_approx(m - m_use);            // m = -inf → 0
-      float rsum = 0.f;
+      m_new = fmaxf(m, mx);
+      m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
+      corr = ex2_approx(m - m_use);            // m = -inf → 0
       // pass 2: P = exp2(s − m), written bf16 + swizzled as the A operand of the P·V MMA
 #pragma unroll 1
       for (int c = 0; c < TK / 32; ++c) {
@@ -202,6 +258,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           pk.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
           *reinterpret_cast<uint4*>(sP + sw128_piece(r, c * 4 + g)) = pk;
         }
+      }
       }
       l = l * corr + rsum;
       m = m_new;
@@ -245,7 +302,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // =========================================================================================== backward
 constexpr int BWD_THREADS = 192;
 // layout: K | V | Q0 | Q1 | dO0 | dO1 | P (2 halves) | dS (2 halves) = 10 tiles
-constexpr int BWD_SMEM = 10 * TILE_BYTES + 1024 + 256;
+constexpr int BWD_SMEM = 10 * TILE_BYTES + 4 * 4096 /* dQ transpose scratch */ + 1024 + 256;
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -262,7 +319,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sdO = smem + 4 * TILE_BYTES;       // 2 stages
   uint8_t* sP = smem + 6 * TILE_BYTES;        // 2 halves
   uint8_t* sdS = smem + 8 * TILE_BYTES;       // 2 halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE_BYTES);
+  uint8_t* sDQ = smem + 10 * TILE_BYTES;      // 4 warps x 4 KB dQ transpose scratch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE_BYTES + 4 * 4096);
   uint64_t *kv_full = bars, *qdo_full = bars + 1, *qdo_empty = bars + 3, *sdp_full = bars + 5, *pds_full = bars + 6,
            *dq_full = bars + 7, *acc_full = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
@@ -358,6 +416,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float dl = row_ok ? delta_row[iq] : 0.f;
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
+      // (key tile, query tile) pairs entirely below the diagonal with every row / key valid need no mask: packed
+      // f32x2 arithmetic, two elements per FFMA2 / FMUL2 (the elementwise threads are issue-bound, see the forward)
+      const bool full_pair = (j0 + TK - 1 <= sh.q_offset + q0) && (j0 + TK <= klen) && (q0 + TQ <= sh.Tq) &&
+                             (sh.q_offset + q0 + TQ <= klen);                         // CTA-uniform
+      const f32x2_t sc2 = splat2(scale2), sl2 = splat2(slope2), scl = splat2(sh.scale), ndl = splat2(-dl * sh.scale);
+      const float rowc = -slope2 * (float)ia - L2;
 #pragma unroll 1
       for (int c = 0; c < TK / 16; ++c) {
         uint32_t vs[16], vp[16];
@@ -365,13 +429,27 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld_32x32b_x16(tdP + lane_addr + c * 16, vp);
         tmem_ld_wait();
         float p[16], ds[16];
+        if (full_pair) {
+          const f32x2_t cb0 = splat2(fmaf(slope2, (float)(j0 + c * 16), rowc));
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int ja = j0 + c * 16 + e;
-          const bool ok = row_ok && ja <= ia && ja < klen;
-          const float s2 = __uint_as_float(vs[e]) * scale2 - slope2 * (float)(ia - ja);
-          p[e] = ok ? ex2_approx(s2 - L2) : 0.f;
-          ds[e] = p[e] * (__uint_as_float(vp[e]) - dl) * sh.scale;
+          for (int e = 0; e < 16; e += 2) {
+            const f32x2_t cb = fma2(sl2, pack2((float)e, (float)(e + 1)), cb0);
+            float a, bq;
+            unpack2(fma2(pack2(__uint_as_float(vs[e]), __uint_as_float(vs[e + 1])), sc2, cb), a, bq);
+            p[e] = ex2_approx(a);
+            p[e + 1] = ex2_approx(bq);
+            const f32x2_t g2 = fma2(pack2(__uint_as_float(vp[e]), __uint_as_float(vp[e + 1])), scl, ndl);
+            unpack2(mul2(pack2(p[e], p[e + 1]), g2), ds[e], ds[e + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int ja = j0 + c * 16 + e;
+            const bool ok = row_ok && ja <= ia && ja < klen;
+            const float s2 = __uint_as_float(vs[e]) * scale2 - slope2 * (float)(ia - ja);
+            p[e] = ok ? ex2_approx(s2 - L2) : 0.f;
+            ds[e] = p[e] * (__uint_as_float(vp[e]) - dl) * sh.scale;
+          }
         }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -391,19 +469,33 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // dQ_i partial of this key tile → fp32 accumulator in global memory
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
-      float* dq_row = dq_acc + ((int64_t)b * sh.Tq + iq) * ((int64_t)sh.H * HD) + h * HD;
+      // thread-per-row vector atomics would touch 32 rows x 16 B per request (32 half-used sectors); each warp
+      // transposes its 32 x 32 chunk through a private 4 KB XOR-swizzled scratch so that eight lanes cover one 128-byte
+      // row segment: a request is four fully used lines
+      {
+        uint8_t* scr = sDQ + (warp & 3) * 4096;
+        const int rows_valid = min(32, max(0, q_valid_end - (q0 + rb)));
+        const int64_t dq_pitch = (int64_t)sh.H * HD;
+        float* dq_base = dq_acc + ((int64_t)b * sh.Tq + q0 + rb) * dq_pitch + h * HD;
 #pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tdQ + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        if (row_ok) {
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tdQ + lane_addr + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 f = make_float4(__uint_as_float(v[g * 4 + 0]), __uint_as_float(v[g * 4 + 1]),
-                                   __uint_as_float(v[g * 4 + 2]), __uint_as_float(v[g * 4 + 3]));
-            atomicAdd(reinterpret_cast<float4*>(dq_row + c * 32 + g * 4), f);
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(scr + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                make_uint4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int row = itr * 4 + (lane >> 3), slot = lane & 7;
+            if (row < rows_valid) {
+              const float4 f = *reinterpret_cast<const float4*>(scr + row * 128 + ((slot ^ (row & 7)) << 4));
+              atomicAdd(reinterpret_cast<float4*>(dq_base + row * dq_pitch + c * 32 + slot * 4), f);
+            }
           }
+          __syncwarp();
         }
       }
       tc_fence_before();
