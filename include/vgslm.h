@@ -277,12 +277,13 @@ int vg_dwconv_ln_fwd(const void* x, const float* w_t, const float* bias /* nulla
                      int64_t B, int64_t T, int64_t C, int32_t taps, int32_t pad_left, float eps, int dtype,
                      vg_stream_t stream);
 size_t vg_dwconv_ln_bwd_workspace(int64_t B, int64_t T, int64_t C, int32_t taps);
-/* dh = dL/d(conv output) [B,T,C] (the caller sums it over T for d t_add); dx = transposed depthwise conv of dh;
- * dw_t [taps][C], d_ln_w, d_ln_b, d_bias [C] are overwritten (deterministic two-stage reduction).              */
+/* dh = dL/d(conv output) [B,T,C]; dx = transposed depthwise conv of dh;
+ * dw_t [taps][C], d_ln_w, d_ln_b, d_bias [C] and d_t_add [B][C] (= sum_t dh, the gradient of the per-sequence time
+ * embedding) are overwritten (deterministic two-stage reductions).                                              */
 int vg_dwconv_ln_bwd(const void* dy, int64_t ld_dy, const void* x, const float* w_t, const float* bias,
                      const float* t_add, const float* ln_w, const float* mean, const float* rstd,
                      void* dh, void* dx, float* dw_t /* nullable iff w_t is NULL */, float* d_ln_w, float* d_ln_b,
-                     float* d_bias /* nullable */, void* workspace, size_t workspace_bytes,
+                     float* d_bias /* nullable */, float* d_t_add /* nullable */, void* workspace, size_t workspace_bytes,
                      int64_t B, int64_t T, int64_t C, int32_t taps, int32_t pad_left, int dtype,
                      vg_stream_t stream);
 

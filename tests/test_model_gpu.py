@@ -157,6 +157,32 @@ def test_bf16_cached_decode_close(golden):
         state = d["outputs"][i][:, -1:].to(DEV)
 
 
+def test_decode_engine_matches_layerwise_path(golden):
+    """the weight-streaming decode engine (decode.py, vg_decode_linear) against the layer-by-layer bf16 step on the
+    same teacher-forced inputs and cache state."""
+    d = golden["decode"]
+    outs = []
+    for use_engine in (False, True):
+        model = build_small(golden, torch.bfloat16).eval()
+        model.use_decode_engine = use_engine
+        model.decode_engine_max_batch = 256
+        model.transformer[0].cache_len_hint = 64
+        o = model.step(d["prompt"].to(DEV), past_kv=None, temperature=0.0, push_init_state=True, greedy=True,
+                       init_state=d["init_state"].to(DEV))
+        state, kv = o["output"][:, -1:], o["kv"]
+        got = []
+        for i in range(6):
+            o = model.step(state, past_kv=kv, temperature=0.0, greedy=True, return_logits=True)
+            got.append((o["logits"].float().cpu(), o["transformer_latent"].value.float().cpu()))
+            kv = o["kv"]
+            state = d["outputs"][min(i + 1, len(d["outputs"]) - 1)][:, -1:].to(DEV)      # teacher-forced inputs
+        assert kv[0].cache.length == d["prompt"].shape[1] + 1 + 6
+        assert ("_decode_engines" in model.__dict__) == use_engine
+        outs.append(got)
+    for (lg0, h0), (lg1, h1) in zip(*outs):
+        assert max_rel(lg1, lg0) < 3e-2 and max_rel(h1, h0) < 3e-2
+
+
 # ------------------------------------------------------------------------- fused latent kernels vs oracle
 def test_latent_kernels_against_oracle(golden):
     sd = {k: v.to(DEV) for k, v in golden["state_dict"].items()}

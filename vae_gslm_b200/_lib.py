@@ -145,7 +145,7 @@ _SIGNATURES = {
     "vg_dwconv_ln_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32,
                                    C.c_int, _p]),
     "vg_dwconv_ln_bwd_workspace": (_sz, [_i64, _i64, _i64, _i32]),
-    "vg_dwconv_ln_bwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
+    "vg_dwconv_ln_bwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                                    _i64, _i64, _i64, _i32, _i32, C.c_int, _p]),
     "vg_softmax_ce_workspace": (_sz, [_i64]),
     "vg_softmax_ce_fwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i64, C.c_int, _p, _sz, _p]),
@@ -161,7 +161,7 @@ _SIGNATURES = {
 
 _lib: Optional[C.CDLL] = None
 launch_count = 0   # kernels of libvgslm launched by this process (bench.py reports it)
-_KERNELS_PER_CALL = {"vg_rmsnorm_bwd": 2, "vg_colsum": 2, "vg_attn_bwd": 3, "vg_latent_front_bwd": 3,
+_KERNELS_PER_CALL = {"vg_rmsnorm_bwd": 2, "vg_colsum": 2, "vg_attn_bwd": 3, "vg_dwconv_ln_bwd": 5, "vg_latent_front_bwd": 3,
                      "vg_latent_back_fwd": 2, "vg_latent_back_bwd": 2, "vg_softmax_ce_fwd": 2, "vg_masked_l1_fwd": 2}
 
 

@@ -107,7 +107,11 @@ dwconv_ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w_t, con
   }
 }
 
-// partial layout per CTA (floats): dw_t [taps][C] | d_ln_w [C] | d_ln_b [C] | d_bias [C]
+// Backward kernel A: dh = dL/d(conv output) per frame, plus the three per-channel sums that only need the frame itself
+// (d_ln_w, d_ln_b, d_bias) accumulated in REGISTERS (each lane owns fixed channels) — the tap gradients, which need the
+// neighbouring frames, are a separate strip kernel (dwconv_wgrad_kernel): accumulating all (taps+3)·C sums in shared
+// memory cost (taps+3)·16 read-modify-writes per lane per frame and made this the slowest kernel of the conv stack.
+// partial layout per CTA (floats): d_ln_w [C] | d_ln_b [C] | d_bias [C]
 template <typename T, int ITERS>
 __global__ void __launch_bounds__(DW_WARPS * 32)
 dwconv_ln_bwd_a_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restrict__ x,
@@ -115,12 +119,14 @@ dwconv_ln_bwd_a_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restr
                        const float* __restrict__ t_add, const float* __restrict__ ln_w,
                        const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dh,
                        float* __restrict__ partial, DwShape s) {
-  extern __shared__ float acc_smem[];            // [DW_WARPS][(taps+3)*C]
+  extern __shared__ float acc_smem[];            // [DW_WARPS][3*C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int np = (s.taps + 3) * s.C;
-  float* acc = acc_smem + warp * np;
-  for (int i = threadIdx.x; i < DW_WARPS * np; i += blockDim.x) acc_smem[i] = 0.f;
-  __syncthreads();
+  const int np = 3 * s.C;
+  float a_w[ITERS][8], a_b[ITERS][8], a_c[ITERS][8];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a_w[it][j] = 0.f; a_b[it][j] = 0.f; a_c[it][j] = 0.f; }
   const int64_t rows = (int64_t)s.B * s.T;
   for (int64_t row = (int64_t)blockIdx.x * DW_WARPS + warp; row < rows; row += (int64_t)gridDim.x * DW_WARPS) {
     const int b = (int)(row / s.T), t = (int)(row % s.T);
@@ -140,8 +146,8 @@ dwconv_ln_bwd_a_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restr
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float hh = (h[it][j] - mu) * r;
-          acc[(s.taps + 0) * s.C + c + j] += dv.v[j] * hh;      // d_ln_w
-          acc[(s.taps + 1) * s.C + c + j] += dv.v[j];           // d_ln_b
+          a_w[it][j] = fmaf(dv.v[j], hh, a_w[it][j]);          // d_ln_w
+          a_b[it][j] += dv.v[j];                               // d_ln_b
           g[it][j] = dv.v[j] * wv.v[j];
           h[it][j] = hh;
           s1 += g[it][j];
@@ -161,19 +167,24 @@ dwconv_ln_bwd_a_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restr
         Vec8<T> o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          g[it][j] = r * (g[it][j] - s1 - h[it][j] * s2);      // dL/d(conv output)
-          o.v[j] = g[it][j];
-          acc[(s.taps + 2) * s.C + c + j] += g[it][j];         // d_bias
+          const float d = r * (g[it][j] - s1 - h[it][j] * s2);      // dL/d(conv output)
+          o.v[j] = d;
+          a_c[it][j] += d;                                     // d_bias
         }
         o.store(dh + row * s.C + c);
-        for (int k = 0; k < s.taps; ++k) {                      // d_w[k][c] += dh * x[t - pad + k]
-          const int tt = t - s.pad_left + k;
-          if (tt < 0 || tt >= s.T) continue;
-          Vec8<T> xv;
-          xv.load(x + ((int64_t)b * s.T + tt) * s.C + c);
+      }
+    }
+  }
+  float* acc = acc_smem + warp * np;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[k * s.C + c + j] += g[it][j] * xv.v[j];
-        }
+  for (int it = 0; it < ITERS; ++it) {
+    const int c = (it * 32 + lane) * 8;
+    if (c < s.C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[c + j] = a_w[it][j];
+        acc[s.C + c + j] = a_b[it][j];
+        acc[2 * s.C + c + j] = a_c[it][j];
       }
     }
   }
@@ -183,6 +194,73 @@ dwconv_ln_bwd_a_kernel(const T* __restrict__ dy, int64_t ld_dy, const T* __restr
 #pragma unroll
     for (int w = 0; w < DW_WARPS; ++w) v += acc_smem[w * np + i];
     partial[(int64_t)blockIdx.x * np + i] = v;
+  }
+}
+
+// Tap gradients and the per-sequence sum of dh (gradient of the time embedding added before the norm):
+//   d_w[k][c] = sum_{b,t} dh[b,t,c] * x[b, t - pad_left + k, c]        d_t[b][c] = sum_t dh[b,t,c]
+// One thread owns 8 channels and walks a strip of DW_STRIP frames of one sequence; the k neighbouring x rows of
+// consecutive frames overlap and come from L1.  partial layout per strip (floats): d_w [taps][C] | sum_dh [C]
+constexpr int DW_STRIP = 16;
+template <typename T>
+__global__ void __launch_bounds__(64)
+dwconv_wgrad_kernel(const T* __restrict__ dh, const T* __restrict__ x, float* __restrict__ partial, DwShape s,
+                    int strips_per_seq) {
+  const int c = (blockIdx.x * 64 + threadIdx.x) * 8;
+  if (c >= s.C) return;
+  const int b = blockIdx.y / strips_per_seq, strip = blockIdx.y - b * strips_per_seq;
+  const int t0 = strip * DW_STRIP, t1 = min(s.T, t0 + DW_STRIP);
+  float aw[DW_MAX_TAPS][8], asum[8];
+#pragma unroll
+  for (int k = 0; k < DW_MAX_TAPS; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) aw[k][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) asum[j] = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    Vec8<T> g;
+    g.load(dh + ((int64_t)b * s.T + t) * s.C + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asum[j] += g.v[j];
+#pragma unroll
+    for (int k = 0; k < DW_MAX_TAPS; ++k) {
+      if (k >= s.taps) break;
+      const int tt = t - s.pad_left + k;
+      if (tt < 0 || tt >= s.T) continue;
+      Vec8<T> xv;
+      xv.load(x + ((int64_t)b * s.T + tt) * s.C + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) aw[k][j] = fmaf(g.v[j], xv.v[j], aw[k][j]);
+    }
+  }
+  float* pp = partial + (int64_t)blockIdx.y * (s.taps + 1) * s.C;
+#pragma unroll
+  for (int k = 0; k < DW_MAX_TAPS; ++k) {
+    if (k >= s.taps) break;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pp[(int64_t)k * s.C + c + j] = aw[k][j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pp[(int64_t)s.taps * s.C + c + j] = asum[j];
+}
+
+// d_w[k][c] = sum over all strips; d_t[b][c] = sum over the strips of sequence b.  Fixed order → deterministic.
+__global__ void __launch_bounds__(256)
+dw_reduce_wgrad_kernel(const float* __restrict__ partial, int B, int strips_per_seq, int taps, int C,
+                       float* __restrict__ dw_t, float* __restrict__ d_t) {
+  const int i = blockIdx.x * 256 + threadIdx.x;            // over (taps + B) * C
+  const int np = (taps + 1) * C;
+  if (i < taps * C) {
+    if (!dw_t) return;
+    float v = 0.f;
+    for (int p = 0; p < B * strips_per_seq; ++p) v += partial[(int64_t)p * np + i];
+    dw_t[i] = v;
+  } else if (i < (taps + B) * C) {
+    if (!d_t) return;
+    const int b = (i - taps * C) / C, c = (i - taps * C) - b * C;
+    float v = 0.f;
+    for (int p = 0; p < strips_per_seq; ++p) v += partial[(int64_t)(b * strips_per_seq + p) * np + taps * C + c];
+    d_t[(int64_t)b * C + c] = v;
   }
 }
 
@@ -236,16 +314,16 @@ dw_reduce_partials_kernel(const float* __restrict__ partial, int nparts, int np,
     float v = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) v += red[g][tx];
-    if (i < taps * C) { if (dw_t) dw_t[i] = v; }
-    else if (i < (taps + 1) * C) d_ln_w[i - taps * C] = v;
-    else if (i < (taps + 2) * C) d_ln_b[i - (taps + 1) * C] = v;
-    else if (d_bias) d_bias[i - (taps + 2) * C] = v;
+    (void)taps; (void)dw_t;
+    if (i < C) d_ln_w[i] = v;
+    else if (i < 2 * C) d_ln_b[i - C] = v;
+    else if (d_bias) d_bias[i - 2 * C] = v;
   }
 }
 
 static int dw_bwd_blocks(int64_t rows) {
   int64_t want = ceil_div(rows, DW_WARPS);
-  int64_t cap = kNumSMs * 2;
+  int64_t cap = kNumSMs * 4;
   return (int)(want < cap ? want : cap);
 }
 
@@ -282,14 +360,17 @@ extern "C" int vg_dwconv_ln_fwd(const void* x, const float* w_t, const float* bi
   return 0;
 }
 
+static size_t dw_partial_a_bytes(int64_t B, int64_t T, int64_t C) {
+  return align_up((size_t)dw_bwd_blocks(B * T) * 3 * (size_t)C * sizeof(float), 256);
+}
 extern "C" size_t vg_dwconv_ln_bwd_workspace(int64_t B, int64_t T, int64_t C, int32_t taps) {
-  return (size_t)dw_bwd_blocks(B * T) * (size_t)(taps + 3) * (size_t)C * sizeof(float);
+  return dw_partial_a_bytes(B, T, C) + (size_t)B * (size_t)ceil_div(T, DW_STRIP) * (size_t)(taps + 1) * (size_t)C * sizeof(float);
 }
 
 extern "C" int vg_dwconv_ln_bwd(const void* dy, int64_t ld_dy, const void* x, const float* w_t, const float* bias,
                                 const float* t_add, const float* ln_w, const float* mean, const float* rstd, void* dh,
-                                void* dx, float* dw_t, float* d_ln_w, float* d_ln_b, float* d_bias, void* workspace,
-                                size_t workspace_bytes, int64_t B, int64_t T, int64_t C, int32_t taps,
+                                void* dx, float* dw_t, float* d_ln_w, float* d_ln_b, float* d_bias, float* d_t_add,
+                                void* workspace, size_t workspace_bytes, int64_t B, int64_t T, int64_t C, int32_t taps,
                                 int32_t pad_left, int dtype, vg_stream_t stream) {
   VG_REQUIRE(dy && x && ln_w && mean && rstd && dh && dx && d_ln_w && d_ln_b, -1, "vg_dwconv_ln_bwd: null pointer");
   if (int rc = dw_check("vg_dwconv_ln_bwd", B, T, C, taps, pad_left, dtype)) return rc;
@@ -300,7 +381,7 @@ extern "C" int vg_dwconv_ln_bwd(const void* dy, int64_t ld_dy, const void* x, co
   DwShape s{(int)B, (int)T, (int)C, taps, pad_left, 0.f};
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = dw_bwd_blocks(B * T);
-  const int np = (taps + 3) * (int)C;
+  const int np = 3 * (int)C;
   const int smem = DW_WARPS * np * (int)sizeof(float);
   const int iters = (int)ceil_div(C, 256);
   float* partial = (float*)workspace;
@@ -310,7 +391,7 @@ extern "C" int vg_dwconv_ln_bwd(const void* dy, int64_t ld_dy, const void* x, co
     static bool attr_set = false;                                                                                 \
     if (!attr_set) {                                                                                              \
       VG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                             \
-                                   DW_WARPS * (DW_MAX_TAPS + 3) * 1024 * (int)sizeof(float)));                    \
+                                   DW_WARPS * 3 * 1024 * (int)sizeof(float)));                                    \
       attr_set = true;                                                                                            \
     }                                                                                                             \
     kern<<<nb, DW_WARPS * 32, smem, st>>>((const TT*)dy, ld_dy, (const TT*)x, w_t, bias, t_add, ln_w, mean, rstd,  \
@@ -323,6 +404,20 @@ extern "C" int vg_dwconv_ln_bwd(const void* dy, int64_t ld_dy, const void* x, co
   dw_reduce_partials_kernel<<<(unsigned)ceil_div(np, 32), 256, 0, st>>>(partial, nb, np, taps, (int)C, dw_t, d_ln_w,
                                                                         d_ln_b, d_bias);
   VG_LAUNCH_CHECK("vg_dwconv_ln_bwd(reduce)");
+  if (dw_t || d_t_add) {          // tap gradients (need the neighbouring frames) + per-sequence sum of dh
+    float* partial_w = (float*)((uint8_t*)workspace + dw_partial_a_bytes(B, T, C));
+    const int sps = (int)ceil_div(T, DW_STRIP);
+    dim3 gw((unsigned)ceil_div(C / 8, 64), (unsigned)(B * sps));
+    if (dtype == VG_F32)
+      dwconv_wgrad_kernel<float><<<gw, 64, 0, st>>>((const float*)dh, (const float*)x, partial_w, s, sps);
+    else
+      dwconv_wgrad_kernel<__nv_bfloat16><<<gw, 64, 0, st>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)x, partial_w,
+                                                           s, sps);
+    VG_LAUNCH_CHECK("vg_dwconv_ln_bwd(wgrad)");
+    dw_reduce_wgrad_kernel<<<(unsigned)ceil_div((int64_t)(taps + B) * C, 256), 256, 0, st>>>(
+        partial_w, (int)B, sps, taps, (int)C, w_t ? dw_t : nullptr, d_t_add);
+    VG_LAUNCH_CHECK("vg_dwconv_ln_bwd(wgrad reduce)");
+  }
   const int64_t n = B * T * (C / 8);
   if (dtype == VG_F32)
     dwconv_bwd_dx_kernel<float><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>((const float*)dh, w_t, (float*)dx, s);

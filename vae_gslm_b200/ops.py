@@ -406,12 +406,12 @@ class _DwConvLN(torch.autograd.Function):
         dw_t = torch.empty((taps, Cc), **f32) if w_t is not None else None
         dlw, dlb = torch.empty(Cc, **f32), torch.empty(Cc, **f32)
         db = torch.empty(Cc, **f32) if has_b else None
+        dt = torch.empty((B, Cc), **f32) if has_t else None          # Σ_t dh, from the strip kernel's partial sums
         ws = L.workspace(L.load().vg_dwconv_ln_bwd_workspace(B, T, Cc, taps), dev)
         L.call("vg_dwconv_ln_bwd", L.ptr(dyc), ld_y, L.ptr(xc), L.ptr(w_t), L.ptr(cb), L.ptr(ta), L.ptr(lw),
                L.ptr(mean), L.ptr(rstd), L.ptr(dh), L.ptr(dx), L.ptr(dw_t), L.ptr(dlw), L.ptr(dlb), L.ptr(db),
-               L.ptr(ws), ws.numel(), B, T, Cc, taps, pad_left, L.dtype_id(xc.dtype), L.stream())
+               L.ptr(dt), L.ptr(ws), ws.numel(), B, T, Cc, taps, pad_left, L.dtype_id(xc.dtype), L.stream())
         dconv_w = dw_t.t().reshape(w_shape) if w_t is not None else None
-        dt = dh.sum(1, dtype=torch.float32) if has_t else None
         return dx, dconv_w, db, dt, dlw, dlb, None, None, None
 
 
