@@ -245,22 +245,36 @@ dwconv_wgrad_kernel(const T* __restrict__ dh, const T* __restrict__ x, float* __
 }
 
 // d_w[k][c] = sum over all strips; d_t[b][c] = sum over the strips of sequence b.  Fixed order → deterministic.
+// One CTA = 32 outputs x 8 groups of partials (shared-memory tree), grid over (taps + B)·C / 32.
 __global__ void __launch_bounds__(256)
 dw_reduce_wgrad_kernel(const float* __restrict__ partial, int B, int strips_per_seq, int taps, int C,
                        float* __restrict__ dw_t, float* __restrict__ d_t) {
-  const int i = blockIdx.x * 256 + threadIdx.x;            // over (taps + B) * C
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;                      // over (taps + B) * C
   const int np = (taps + 1) * C;
+  float v = 0.f;
+  bool live = false;
+  float* dst = nullptr;
   if (i < taps * C) {
-    if (!dw_t) return;
-    float v = 0.f;
-    for (int p = 0; p < B * strips_per_seq; ++p) v += partial[(int64_t)p * np + i];
-    dw_t[i] = v;
+    live = dw_t != nullptr;
+    dst = dw_t + i;
+    if (live)
+      for (int p = ty; p < B * strips_per_seq; p += 8) v += partial[(int64_t)p * np + i];
   } else if (i < (taps + B) * C) {
-    if (!d_t) return;
     const int b = (i - taps * C) / C, c = (i - taps * C) - b * C;
-    float v = 0.f;
-    for (int p = 0; p < strips_per_seq; ++p) v += partial[(int64_t)(b * strips_per_seq + p) * np + taps * C + c];
-    d_t[(int64_t)b * C + c] = v;
+    live = d_t != nullptr;
+    dst = d_t + (int64_t)b * C + c;
+    if (live)
+      for (int p = ty; p < strips_per_seq; p += 8) v += partial[(int64_t)(b * strips_per_seq + p) * np + taps * C + c];
+  }
+  red[ty][tx] = v;
+  __syncthreads();
+  if (ty == 0 && live) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][tx];
+    *dst = t;
   }
 }
 
@@ -414,7 +428,7 @@ extern "C" int vg_dwconv_ln_bwd(const void* dy, int64_t ld_dy, const void* x, co
       dwconv_wgrad_kernel<__nv_bfloat16><<<gw, 64, 0, st>>>((const __nv_bfloat16*)dh, (const __nv_bfloat16*)x, partial_w,
                                                            s, sps);
     VG_LAUNCH_CHECK("vg_dwconv_ln_bwd(wgrad)");
-    dw_reduce_wgrad_kernel<<<(unsigned)ceil_div((int64_t)(taps + B) * C, 256), 256, 0, st>>>(
+    dw_reduce_wgrad_kernel<<<(unsigned)ceil_div((int64_t)(taps + B) * C, 32), 256, 0, st>>>(
         partial_w, (int)B, sps, taps, (int)C, w_t ? dw_t : nullptr, d_t_add);
     VG_LAUNCH_CHECK("vg_dwconv_ln_bwd(wgrad reduce)");
   }

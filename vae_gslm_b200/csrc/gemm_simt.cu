@@ -107,7 +107,7 @@ int gemm_simt_launch(const vg_gemm_args* a, cudaStream_t st) {
 // ---- column sums (bias gradients) ----------------------------------------------------------------
 // stage 1: each thread owns 8 consecutive columns (one 16-byte load per row) and walks a strip of rows;
 // stage 2: fixed-order sum of the strip partials.  HBM-bound: the matrix is read exactly once.
-constexpr int kColsumRowsPerBlock = 64;
+constexpr int kColsumRowsPerBlock = 32;
 
 template <typename T>
 __global__ void __launch_bounds__(128)

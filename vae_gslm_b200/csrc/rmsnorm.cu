@@ -62,13 +62,10 @@ rmsnorm_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const fl
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float acc[ITERS][8];
-  Vec8<float> sc[ITERS];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
-    const int c = (it * 32 + lane) * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[it][j] = 0.f;
-    if (c < dim) sc[it].load(scale + c);
   }
   for (int64_t row = (int64_t)blockIdx.x * kRmsWarps + warp; row < rows;
        row += (int64_t)gridDim.x * kRmsWarps) {
@@ -83,12 +80,14 @@ rmsnorm_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const fl
       if (c < dim) {
         xv[it].load(x + row * dim + c);
         gv[it].load(dy + row * dim + c);
+        Vec8<float> sc;                    // re-read per row (L1-resident): keeping it in registers spilled at dim 1024
+        sc.load(scale + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float g = keep ? gv[it].v[j] : 0.f;
           const float xh = xv[it].v[j] * r;
           acc[it][j] += g * xh;
-          gv[it].v[j] = g * sc[it].v[j];   // dL/d(xhat)
+          gv[it].v[j] = g * sc.v[j];       // dL/d(xhat)
           xv[it].v[j] = xh;
           dot += gv[it].v[j] * xh;
         }

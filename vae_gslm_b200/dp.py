@@ -37,6 +37,9 @@ class GradReducer:
         self.is_cuda = self.buckets[0][0].is_cuda
         self.comm_stream = torch.cuda.Stream() if self.is_cuda else None
         self._launched: List[bool] = []
+        # streams other than the current one on which gradients of a bucket may still be in flight when the bucket's
+        # last gradient is announced (LVTR runs the utterance encoder / diffusion decoder branch on a side stream)
+        self.extra_streams: List["torch.cuda.Stream"] = []
         for _, members in self.buckets:
             for p in members:                 # autograd-accumulated gradients announce themselves through a hook;
                 p.register_post_accumulate_grad_hook(self._hook)
@@ -69,6 +72,8 @@ class GradReducer:
         flat = self.buckets[bi][0]
         if self.is_cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
+            for st in self.extra_streams:
+                self.comm_stream.wait_stream(st)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
         else:       # gloo (CPU tests): no AVG op

@@ -94,6 +94,7 @@ class LVTR(nn.Module):
                 TimeAggregation())
         self.use_tokens = self.tokens is not None
         self.compute_dtype = torch.float32
+        self.overlap_decoder = True         # diffusion decoder branch on a side stream (parallel graph branch)
         self.use_decode_engine = True       # bf16 single-frame steps run on decode.DecodeEngine ...
         # ... up to this batch: measured on B200 (profiles/r01_decode.md) the weight-streaming engine wins below ~48
         # sequences (0.57 vs 1.21 ms per step at B=1), the tcgen05 layer-by-layer path above (2.0 vs 3.7 ms at B=256)
@@ -180,6 +181,18 @@ class LVTR(nn.Module):
         B, T = mask.shape
         dev = mel.value.device
         Ld = self.hp.latent_dim
+        # The utterance encoder (strided convs over <= 200 frames: ~100 tiny launches fwd + bwd) does not meet the
+        # main path until the diffusion decoder: run it on a side stream (a parallel branch of the captured graph;
+        # autograd replays its backward on the same stream) so that it hides behind the transformer GEMMs.
+        u_c, side = None, None
+        if self.utterance_encoder is not None:
+            if mel.value.is_cuda:
+                side = self.__dict__.setdefault("_side_stream", torch.cuda.Stream(device=dev))
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side), self._autocast():
+                    u_c = self.utterance_encoder(utterance)
+            else:
+                u_c = self.utterance_encoder(utterance)
         with self._autocast():
             h_enc = self.encoder[0](mel).value.float()
         # RNG draws #1..#3 in the reference's order (lvtr.py:156,161,172)
@@ -194,21 +207,39 @@ class LVTR(nn.Module):
             h_enc, eps_q, tokens_id.value, mask, init_state.reshape(B, -1), post.mean.weight, post.mean.bias,
             post.logstd.weight, post.logstd.bias, self.token_embedding.weight, fuser.weight, fuser.bias,
             1.0, self.compute_dtype)
+        # diffusion decoder on fuse(z, tokens) ⊕ utterance embedding (lvtr.py:201-209).  It depends on the posterior
+        # sample only, not on the transformer: with `overlap_decoder` it runs on the side stream, concurrently with the
+        # transformer stack (a parallel branch of the captured graph, forward and backward) — its many short kernels
+        # fill the gaps of the big GEMMs instead of extending the critical path.
+        def run_decoder():
+            cond = u
+            if u_c is not None:
+                cond = torch.cat([cond, u_c.to(cond.dtype)[:, None].expand(-1, T, -1)], -1)
+            with self._autocast():
+                return self.decoder(mel / self.diff_scaling, TensorMask(cond, mask), t=diff_t, noise=diff_noise)
+
+        rec_x = None
+        main = torch.cuda.current_stream() if side is not None else None
+        if side is not None and self.overlap_decoder:
+            side.wait_stream(main)                       # u (and the RNG draws above) are ordered before the branch
+            for t_ in (u, mel.value, mask):
+                t_.record_stream(side)
+            with torch.cuda.stream(side):
+                rec_x = run_decoder()
         transformer_latent = self.transformer[0](TensorMask(u_shift, mask), c)
         c_lat, head, logits = self._post_stack(transformer_latent.value)
         flow = self.transformer_flow
         lo, hi = flow.scale_lo_hi
         log_p, sample_p, kl_sum = ops.latent_back(head, z, log_q, mask, *flow.stacked_parameters(), flow.ln_eps, lo, hi)
         ce_loss = ops.softmax_ce(logits, tokens_id.value, mask)
-        # diffusion decoder on fuse(z, tokens) ⊕ utterance embedding
-        cond = u
-        u_c = None
-        if self.utterance_encoder is not None:
-            with self._autocast():
-                u_c = self.utterance_encoder(utterance)
-            cond = torch.cat([cond, u_c.to(cond.dtype)[:, None].expand(-1, T, -1)], -1)
-        with self._autocast():
-            rec_x = self.decoder(mel / self.diff_scaling, TensorMask(cond, mask), t=diff_t, noise=diff_noise)
+        if side is not None:
+            main.wait_stream(side)
+            if u_c is not None:
+                u_c.record_stream(main)
+            if rec_x is not None:
+                (rec_x.value if isinstance(rec_x, TensorMask) else rec_x).record_stream(main)
+        if rec_x is None:
+            rec_x = run_decoder()
         q_z = AttrDict(mean=TensorMask(mean_q, mask), logstd=TensorMask(logstd_q, mask), sample=TensorMask(z, mask))
         with torch.no_grad():
             hd = head.detach()

@@ -93,6 +93,9 @@ class TrainStep:
     # the work of one step, on whatever stream is current
     def _body(self, device_hyper: bool) -> None:
         s = self.static
+        side = self.model.__dict__.get("_side_stream")
+        if side is not None and side not in self.reducer.extra_streams:
+            self.reducer.extra_streams.append(side)
         self.arena.zero_grad()
         self.reducer.prepare(last_micro_batch=True)
         out = self.model(TensorMask(s["x"], s["mask"]), utterance=TensorMask(s["utterance"], s["utt_mask"]))
