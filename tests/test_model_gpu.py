@@ -183,6 +183,38 @@ def test_decode_engine_matches_layerwise_path(golden):
         assert max_rel(lg1, lg0) < 3e-2 and max_rel(h1, h0) < 3e-2
 
 
+def test_train_step_overlapped_graph_matches_serial_eager(golden):
+    """TrainStep (trainers/speech/lvtr.py): the captured step with the parameter-gradient side stream and the
+    diffusion-decoder branch on its own stream must reproduce the fully serial eager step.  Same weights, batch and
+    injected RNG draws; construction / warm-up / capture run with lr = 0 (Adam's bias-corrected moments of a repeated
+    gradient do not depend on how many warm-up steps ran), then ONE update with lr > 0 is compared."""
+    from vae_gslm_b200.arena import ParamArena
+    from vae_gslm_b200.dp import GradReducer
+    from vae_gslm_b200.trainers.speech.lvtr import TrainStep
+    i = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in golden["inputs"].items()}
+    batch = {k: i[k] for k in ("x", "mask", "utterance", "utt_mask")}
+    draws = {k: i[k] for k in ("eps_q", "init_state", "eps_p", "diff_t", "diff_noise")}
+    runs = []
+    for overlapped in (False, True):
+        model = build_small(golden, torch.bfloat16)
+        model.overlap_decoder = overlapped
+        inner = model.forward
+        model.forward = lambda x, _f=inner, **kw: _f(x, **kw, **draws)
+        arena = ParamArena(model, weight_decay=0.1)
+        step = TrainStep(model, arena, GradReducer(arena), batch, lr=0.0, kld_weight=0.04,
+                         use_cuda_graph=overlapped, overlap_grads=overlapped, warmup_iters=1)
+        assert (step.graph is not None) == overlapped, step.capture_error
+        before = torch.cat([g.p.detach().float().cpu() for g in arena.groups])
+        loss = float(step(lr=1e-3))
+        after = torch.cat([g.p.detach().float().cpu() for g in arena.groups])
+        assert float((after - before).abs().max()) > 1e-4          # the update happened
+        runs.append((loss, after, torch.cat([g.g.detach().float().cpu() for g in arena.groups])))
+    (l0, p0, g0), (l1, p1, g1) = runs
+    assert abs(l0 - l1) <= 2e-3 * abs(l0), (l0, l1)
+    assert max_rel(g1, g0) < 2e-2            # every parameter gradient (bf16 atomics / split-K order noise only)
+    assert max_rel(p1, p0) < 1e-2
+
+
 # ------------------------------------------------------------------------- fused latent kernels vs oracle
 def test_latent_kernels_against_oracle(golden):
     sd = {k: v.to(DEV) for k, v in golden["state_dict"].items()}

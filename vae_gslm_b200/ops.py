@@ -144,14 +144,44 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None, beta: float = 0.
     return out
 
 
+# Parameter gradients (wgrad GEMMs, bias column sums) are off the critical path of backward: nothing downstream reads
+# them before the optimizer.  With GRAD_STREAM set (TrainStep does) they are enqueued on that side stream — in a captured
+# graph a parallel branch — so the memory-bound column sums run under the compute-bound dgrad GEMMs and the wgrad GEMMs
+# fill the tail waves of the dgrad GEMMs.  The owner of the stream joins it before the optimizer / all-reduce.
+GRAD_STREAM = None
+
+
+class _on_grad_stream:
+    def __init__(self, *tensors):
+        self.tensors = tensors
+        self.ctx = None
+
+    def __enter__(self):
+        gs = GRAD_STREAM
+        if gs is None or not self.tensors[0].is_cuda:
+            return self
+        gs.wait_stream(torch.cuda.current_stream())
+        for t in self.tensors:
+            t.record_stream(gs)
+        self.ctx = torch.cuda.stream(gs)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 def _bgrad(dy2: torch.Tensor, bias: torch.Tensor) -> Optional[torch.Tensor]:
     """db = Σ_rows dy.  A bias that lives in a ParamArena gets the sum written (or accumulated, on later
     micro-batches) straight into its gradient slice and autograd receives None — no AccumulateGrad add kernel."""
     main = getattr(bias, "_vg_main_grad", None)
     if main is not None:
         arena = bias._vg_arena
-        colsum(dy2, out=main, beta=arena.wgrad_beta())
-        arena.grad_ready(bias)
+        with _on_grad_stream(dy2):
+            colsum(dy2, out=main, beta=arena.wgrad_beta())
+            arena.grad_ready(bias)
         return None
     return colsum(dy2)
 
@@ -264,8 +294,9 @@ def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor) -> Optiona
     main = getattr(weight, "_vg_main_grad", None)
     if main is not None:
         arena = weight._vg_arena
-        gemm(dy2, x2, trans_a=True, trans_b=False, out=main.view(main.shape[0], -1), beta=arena.wgrad_beta())
-        arena.grad_ready(weight)
+        with _on_grad_stream(dy2, x2):
+            gemm(dy2, x2, trans_a=True, trans_b=False, out=main.view(main.shape[0], -1), beta=arena.wgrad_beta())
+            arena.grad_ready(weight)
         return None
     dw = gemm(dy2, x2, trans_a=True, trans_b=False, out_dtype=torch.float32).view(weight.shape)   # 1x1 conv: [N,K,1]
     return dw if weight.dtype == torch.float32 else dw.to(weight.dtype)

@@ -56,7 +56,7 @@ class TrainStep:
 
     def __init__(self, model, arena, reducer, example_batch: Dict[str, torch.Tensor], *, lr: float,
                  kld_weight: float = 0.04, betas=(0.9, 0.98), eps: float = 1e-8, use_cuda_graph: bool = True,
-                 warmup_iters: int = 3) -> None:
+                 warmup_iters: int = 3, overlap_grads: bool = True) -> None:
         self.model, self.arena, self.reducer = model, arena, reducer
         self.lr, self.betas, self.eps = lr, betas, eps
         self.static = {k: v.clone() for k, v in example_batch.items()}        # device-resident input buffers
@@ -65,6 +65,8 @@ class TrainStep:
         self.loss = torch.zeros((), device=dev)
         self.terms = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.grad_stream = None
+        self.overlap_grads = overlap_grads
         self.mode = "eager"
         self.capture_error: Optional[str] = None
         # Every execution of the step body — warm-up, capture, eager — runs on ONE private stream.  autograd's
@@ -93,14 +95,21 @@ class TrainStep:
     # the work of one step, on whatever stream is current
     def _body(self, device_hyper: bool) -> None:
         s = self.static
-        side = self.model.__dict__.get("_side_stream")
-        if side is not None and side not in self.reducer.extra_streams:
-            self.reducer.extra_streams.append(side)
+        from ... import ops
+        if self.grad_stream is None and self.loss.is_cuda and self.overlap_grads:
+            self.grad_stream = torch.cuda.Stream(device=self.loss.device)
+        for side in (self.model.__dict__.get("_side_stream"), self.grad_stream):
+            if side is not None and side not in self.reducer.extra_streams:
+                self.reducer.extra_streams.append(side)
+        ops.GRAD_STREAM = self.grad_stream
         self.arena.zero_grad()
         self.reducer.prepare(last_micro_batch=True)
         out = self.model(TensorMask(s["x"], s["mask"]), utterance=TensorMask(s["utterance"], s["utt_mask"]))
         terms = assemble_loss(out, kld_weight=self.kw_dev)
         terms["loss"].backward()
+        ops.GRAD_STREAM = None
+        if self.grad_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.grad_stream)     # parameter gradients are complete
         self.reducer.finish()
         self.arena.adamw_step(self.lr, self.betas[0], self.betas[1], self.eps, use_device_hyper=device_hyper)
         self.loss.copy_(terms["loss"].detach())
