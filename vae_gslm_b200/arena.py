@@ -145,15 +145,37 @@ class ParamArena:
     def buckets(self, bucket_bytes: int = 64 << 20) -> List[Tuple[torch.Tensor, List[nn.Parameter]]]:
         """contiguous gradient slices of ~bucket_bytes with the parameters they hold, in arena order."""
         out = []
-        for grp in self.groups:
+        self.bucket_ranges: List[Tuple[int, int, int]] = []      # (group index, start, end) per bucket
+        for gi, grp in enumerate(self.groups):
             start, members = 0, []
             for i, p in enumerate(grp.params):
                 end = grp.offsets[i + 1] if i + 1 < len(grp.params) else grp.numel
                 members.append(p)
                 if (end - start) * 4 >= bucket_bytes or i + 1 == len(grp.params):
                     out.append((grp.g[start:end], members))
+                    self.bucket_ranges.append((gi, start, end))
                     start, members = end, []
         return out
+
+    def begin_step(self, lr: float, beta1: float = 0.9, beta2: float = 0.98, use_device_hyper: bool = False):
+        """advance the step counter and stage this step's scalars; must precede the first adamw_bucket()."""
+        self._bc = self.stage_hyper(lr, beta1, beta2)
+        self._step_args = (lr, beta1, beta2, use_device_hyper)
+        if use_device_hyper:
+            for hyper, host in zip(self.hyper, self._hyper_host):
+                hyper.copy_(host, non_blocking=True)
+
+    def adamw_bucket(self, bucket_index: int, eps: float = 1e-8, grad_scale: float = 1.0) -> None:
+        """AdamW (+ bf16 shadow refresh) of ONE bucket of buckets(): lets the optimizer run, bucket by bucket, as soon as
+        a bucket's gradients are final (and all-reduced) — HBM-bound work hidden under the rest of backward."""
+        gi, start, end = self.bucket_ranges[bucket_index]
+        grp = self.groups[gi]
+        lr, beta1, beta2, dev_hyper = self._step_args
+        bc1, bc2 = self._bc
+        sl = slice(start, end)
+        L.call("vg_adamw_step", L.ptr(grp.p[sl]), L.ptr(grp.g[sl]), L.ptr(grp.m[sl]), L.ptr(grp.v[sl]),
+               L.ptr(grp.shadow[sl]) if grp.shadow is not None else None, end - start, lr, beta1, beta2, eps,
+               grp.weight_decay, bc1, bc2, grad_scale, L.ptr(self.hyper[gi]) if dev_hyper else None, L.stream())
 
     def total_numel(self) -> int:
         return sum(g.numel for g in self.groups)

@@ -34,6 +34,9 @@ class GradReducer:
                 self._bucket_of[id(p)] = bi
         self._handles = []
         self.enabled = False           # armed only for the micro-batch that closes an accumulation window
+        # optional callable(bucket_index) enqueued on the communication stream right after a bucket's all-reduce:
+        # TrainStep installs the bucket-wise AdamW there, so the optimizer overlaps the rest of backward too
+        self.after_bucket = None
         self.is_cuda = self.buckets[0][0].is_cuda
         self.comm_stream = torch.cuda.Stream() if self.is_cuda else None
         self._launched: List[bool] = []
@@ -46,8 +49,17 @@ class GradReducer:
         arena.on_grad_ready = self._ready     # gradients written directly by ops._wgrad/_bgrad/_RMSNorm call this
 
     # ------------------------------------------------------------------ per-backward protocol
+    def calibrate_next(self) -> None:
+        """count, during the next backward, how many times each parameter's gradient is announced (a parameter used
+        twice in the graph is announced twice) and use those counts afterwards: a bucket must not be reduced / stepped
+        before its LAST contribution.  The calibration backward launches nothing early."""
+        self._calibrating = True
+        self._seen: Dict[int, int] = {}
+
     def prepare(self, last_micro_batch: bool = True) -> None:
-        self.enabled = last_micro_batch and self.world > 1
+        # armed on the micro-batch that closes an accumulation window, when there is something to do per bucket:
+        # an all-reduce (world > 1) and / or the bucket-wise optimizer step (after_bucket)
+        self.enabled = last_micro_batch and (self.world > 1 or self.after_bucket is not None)
         self._pending = list(self._size)
         self._launched = [False] * len(self.buckets)
         self._handles = []
@@ -60,6 +72,9 @@ class GradReducer:
             return
         bi = self._bucket_of.get(id(param))
         if bi is None:
+            return
+        if getattr(self, "_calibrating", False):
+            self._seen[id(param)] = self._seen.get(id(param), 0) + 1
             return
         self._pending[bi] -= 1
         if self._pending[bi] == 0 and self.overlap:
@@ -75,22 +90,32 @@ class GradReducer:
             for st in self.extra_streams:
                 self.comm_stream.wait_stream(st)
             with torch.cuda.stream(self.comm_stream):
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
-        else:       # gloo (CPU tests): no AVG op
+                if self.world > 1:
+                    dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+                if self.after_bucket is not None:
+                    self.after_bucket(bi)
+        elif self.world > 1:       # gloo (CPU tests): no AVG op
             h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self._handles.append((h, flat))
+            self._handles.append((h, flat, bi))
+        elif self.after_bucket is not None:
+            self.after_bucket(bi)
 
     def finish(self) -> None:
         """reduce whatever has not been launched yet (parameters unused in this step never fire a hook) and make
         the compute stream wait for the collectives."""
         if not self.enabled:
             return
+        if getattr(self, "_calibrating", False):
+            self._calibrating = False
+            self._size = [sum(self._seen.get(id(p), 0) for p in members) for _, members in self.buckets]
         for bi in range(len(self.buckets)):
             self._launch(bi)
         if self.is_cuda:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         else:
-            for h, flat in self._handles:
+            for h, flat, bi in self._handles:
                 h.wait()
                 flat.div_(self.world)
+                if self.after_bucket is not None:
+                    self.after_bucket(bi)
         self.enabled = False

@@ -67,6 +67,7 @@ class TrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.grad_stream = None
         self.overlap_grads = overlap_grads
+        self.overlap_optimizer = overlap_grads          # bucket-wise AdamW behind each bucket's all-reduce
         self.mode = "eager"
         self.capture_error: Optional[str] = None
         # Every execution of the step body — warm-up, capture, eager — runs on ONE private stream.  autograd's
@@ -76,6 +77,8 @@ class TrainStep:
         self.stream = torch.cuda.Stream(device=dev)
         from ... import _lib
         n0 = _lib.launch_count
+        if hasattr(self.reducer, "calibrate_next"):
+            self.reducer.calibrate_next()                   # first step: learn how often each gradient is announced
         self._run_eager(device_hyper=False)                 # also the first warm-up iteration
         self.launches_per_step = _lib.launch_count - n0     # libvgslm kernels per step (bench.py's gpu_launches)
         if use_cuda_graph:
@@ -103,6 +106,10 @@ class TrainStep:
                 self.reducer.extra_streams.append(side)
         ops.GRAD_STREAM = self.grad_stream
         self.arena.zero_grad()
+        if self.overlap_optimizer:
+            # bucket-wise AdamW on the communication stream, right behind each bucket's all-reduce
+            self.arena.begin_step(self.lr, self.betas[0], self.betas[1], use_device_hyper=device_hyper)
+            self.reducer.after_bucket = lambda bi: self.arena.adamw_bucket(bi, eps=self.eps)
         self.reducer.prepare(last_micro_batch=True)
         out = self.model(TensorMask(s["x"], s["mask"]), utterance=TensorMask(s["utterance"], s["utt_mask"]))
         terms = assemble_loss(out, kld_weight=self.kw_dev)
@@ -111,7 +118,8 @@ class TrainStep:
         if self.grad_stream is not None:
             torch.cuda.current_stream().wait_stream(self.grad_stream)     # parameter gradients are complete
         self.reducer.finish()
-        self.arena.adamw_step(self.lr, self.betas[0], self.betas[1], self.eps, use_device_hyper=device_hyper)
+        if not self.overlap_optimizer:
+            self.arena.adamw_step(self.lr, self.betas[0], self.betas[1], self.eps, use_device_hyper=device_hyper)
         self.loss.copy_(terms["loss"].detach())
 
     def _capture(self, warmup_iters: int) -> None:
