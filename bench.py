@@ -190,7 +190,8 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (gemm_tc_kernel): one extra, instrumented step (not part of the timing)
     ops.PROFILE = []
-    train_step._run_eager(device_hyper=False)                # eager on purpose: CUDA events around every GEMM launch
+    # eager and serial on purpose (no side streams): CUDA events around every GEMM launch, one kernel at a time
+    train_step._run_eager(device_hyper=False, serial=True)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in prof)
@@ -366,7 +367,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="sequences per GPU (repo config: 8)")

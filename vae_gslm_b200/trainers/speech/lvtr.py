@@ -89,11 +89,19 @@ class TrainStep:
                 self.graph = None
                 self.capture_error = repr(e)
 
-    def _run_eager(self, device_hyper: bool) -> None:
+    def _run_eager(self, device_hyper: bool, serial: bool = False) -> None:
+        """one eager step; ``serial`` switches every stream overlap off (bench.py's per-kernel timing pass)."""
+        saved = (self.overlap_grads, self.overlap_optimizer, self.grad_stream, self.model.overlap_decoder)
+        if serial:
+            self.overlap_grads = self.overlap_optimizer = False
+            self.grad_stream, self.model.overlap_decoder = None, False
+            self.reducer.after_bucket = None
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             self._body(device_hyper)
         torch.cuda.current_stream().wait_stream(self.stream)
+        if serial:
+            self.overlap_grads, self.overlap_optimizer, self.grad_stream, self.model.overlap_decoder = saved
 
     # the work of one step, on whatever stream is current
     def _body(self, device_hyper: bool) -> None:
