@@ -7,7 +7,7 @@ import torch
 from vae_gslm_b200 import _lib as L, ops
 
 dev = "cuda"
-for (B, T, H) in [(8, 1000, 16), (8, 640, 16), (2, 3000, 16)]:
+for (B, T, H) in [(8, 1000, 16), (8, 1000, 16), (8, 640, 16), (2, 3000, 16)]:
     qkv = (0.5 * torch.randn(B, T, 3 * H * 64, device=dev)).to(torch.bfloat16).requires_grad_(True)
     slopes = torch.tensor(ops.alibi_slopes(H), device=dev)
     lengths = torch.full((B,), T, device=dev, dtype=torch.int32)

@@ -20,6 +20,8 @@ model = LVTR(hp.model, input_dim=bench.N_MELS)
 model.apply(init_weights)
 model = model.to(dev).set_compute_dtype(torch.bfloat16).eval()
 batches = tuple(int(a) for a in sys.argv[1:] if a.isdigit()) or (1, 8, 64, 256)
+if "--force-engine" in sys.argv:
+    model.decode_engine_max_batch = 256
 for engine in ((True, False) if "--both" in sys.argv else (True,)):
     model.use_decode_engine = engine
     out = bench.decode_bench(model, dev, bench.measured_peaks(), batches=batches)

@@ -300,9 +300,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // =========================================================================================== backward
-constexpr int BWD_THREADS = 192;
+constexpr int BWD_THREADS = 320;            // 2 control warps + 8 elementwise warps (two per TMEM lane quadrant)
 // layout: K | V | Q0 | Q1 | dO0 | dO1 | P (2 halves) | dS (2 halves) = 10 tiles
-constexpr int BWD_SMEM = 10 * TILE_BYTES + 4 * 4096 /* dQ transpose scratch */ + 1024 + 256;
+constexpr int BWD_SMEM = 10 * TILE_BYTES + 8 * 4096 /* dQ transpose scratch */ + 1024 + 256;
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -319,8 +319,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sdO = smem + 4 * TILE_BYTES;       // 2 stages
   uint8_t* sP = smem + 6 * TILE_BYTES;        // 2 halves
   uint8_t* sdS = smem + 8 * TILE_BYTES;       // 2 halves
-  uint8_t* sDQ = smem + 10 * TILE_BYTES;      // 4 warps x 4 KB dQ transpose scratch
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE_BYTES + 4 * 4096);
+  uint8_t* sDQ = smem + 10 * TILE_BYTES;      // 8 warps x 4 KB dQ transpose scratch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE_BYTES + 8 * 4096);
   uint64_t *kv_full = bars, *qdo_full = bars + 1, *qdo_empty = bars + 3, *sdp_full = bars + 5, *pds_full = bars + 6,
            *dq_full = bars + 7, *acc_full = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
@@ -341,7 +341,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(kv_full, 1);
     mbar_init(&qdo_full[0], 1); mbar_init(&qdo_full[1], 1);
     mbar_init(&qdo_empty[0], 1); mbar_init(&qdo_empty[1], 1);
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 128); mbar_init(dq_full, 1); mbar_init(acc_full, 1);
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(dq_full, 1); mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -400,7 +400,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (n_it > 0) umma_commit(acc_full);
   } else if (warp >= 2) {
     // ===================== softmax-backward threads (thread = query row of the current tile) =====================
+    // warps 2..9: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.  With one warp per
+    // scheduler the elementwise phase was latency-bound (~10 k cycles per tile pair against 1.3 k cycles of MMA).
     const int rb = (warp & 3) * 32;
+    const int half = (warp - 2) >> 2;
     const int r = rb + lane;
     const uint32_t lane_addr = (uint32_t)rb << 16;
     const float slope2 = (slopes ? slopes[h] : 0.f) * kLog2e;
@@ -423,7 +426,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const f32x2_t sc2 = splat2(scale2), sl2 = splat2(slope2), scl = splat2(sh.scale), ndl = splat2(-dl * sh.scale);
       const float rowc = -slope2 * (float)ia - L2;
 #pragma unroll 1
-      for (int c = 0; c < TK / 16; ++c) {
+      for (int c = half * (TK / 32); c < (half + 1) * (TK / 32); ++c) {
         uint32_t vs[16], vp[16];
         tmem_ld_32x32b_x16(tS + lane_addr + c * 16, vs);
         tmem_ld_32x32b_x16(tdP + lane_addr + c * 16, vp);
@@ -473,12 +476,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // transposes its 32 x 32 chunk through a private 4 KB XOR-swizzled scratch so that eight lanes cover one 128-byte
       // row segment: a request is four fully used lines
       {
-        uint8_t* scr = sDQ + (warp & 3) * 4096;
+        uint8_t* scr = sDQ + (warp - 2) * 4096;
         const int rows_valid = min(32, max(0, q_valid_end - (q0 + rb)));
         const int64_t dq_pitch = (int64_t)sh.H * HD;
         float* dq_base = dq_acc + ((int64_t)b * sh.Tq + q0 + rb) * dq_pitch + h * HD;
-#pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
+        {
+          const int c = half;                      // this warp's 32 of the 64 head-dim columns
           uint32_t v[32];
           tmem_ld_32x32b_x32(tdQ + lane_addr + c * 32, v);
           tmem_ld_wait();
@@ -510,8 +513,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int which = 0; which < 2; ++which) {
       __nv_bfloat16* dst = (which == 0 ? dv : dk) + ((int64_t)b * sh.Tk + jr) * ld_dkv + h * HD;
       const uint32_t tsrc = (which == 0 ? tdV : tdK) + lane_addr;
-#pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
+      {
+        const int c = half;
         uint32_t v[32];
         if (n_it > 0) {
           tmem_ld_32x32b_x32(tsrc + c * 32, v);

@@ -98,11 +98,21 @@ __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
+// bias + activation + residual of one output element.  Deliberately NOT inlined: the epilogue calls it eight times and
+// the body then runs from the instruction cache (this kernel executes every code path exactly once per CTA, so
+// straight-line code is a chain of cold instruction-cache misses).
+__device__ __noinline__ float dl_finish_elem(float t, const float* bias_ptr, int act, const __nv_bfloat16* res_ptr) {
+  if (bias_ptr) t += *bias_ptr;
+  if (act != VG_ACT_NONE) t = apply_act(t, act);
+  if (res_ptr) t += __bfloat162float(*res_ptr);
+  return t;
+}
+
 // NTC = n8-tiles per CTA (Nc = 8·NTC features).  Grid = feature ranges x ksplit; the ksplit CTAs of one feature
 // range form a thread-block cluster and reduce their k-slices through distributed shared memory.
 template <int NTC>
 __global__ void __launch_bounds__(DL_THREADS)
-decode_linear_kernel(DlParams p) {
+decode_linear_kernel(const __grid_constant__ DlParams p) {
   extern __shared__ __align__(16) uint8_t dl_smem[];
   constexpr int Nc = NTC * 8;
   const int KLP = p.KL + DL_PAD;
@@ -119,6 +129,17 @@ decode_linear_kernel(DlParams p) {
   const uint32_t row_bytes = (uint32_t)p.KL * 2;
 
   DL_STAMP(0);
+  // Kernel parameters live in the constant bank and every launch starts with a cold constant cache: the epilogue's
+  // first touch of bias / act / residual / ldy ... was a chain of dependent ~500-cycle misses (2.6 k cycles measured).
+  // Touch every 64-byte line of the parameter block now, while nothing depends on it.
+  {
+    const uint32_t* pw = reinterpret_cast<const uint32_t*>(&p);
+    uint32_t sink = 0;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(DlParams) / 4); i += 16) sink |= pw[i];
+    sink |= pw[sizeof(DlParams) / 4 - 1];
+    if (sink == 0x7fc0dead && p.trace) p.trace[39] = sink;      // never true in practice; keeps the loads alive
+  }
   pdl_launch_dependents();                         // the next kernel may begin ITS weight prefetch
   if (tid == 0) {
     dl_mbar_init(&bars[0], 1);
@@ -173,7 +194,10 @@ decode_linear_kernel(DlParams p) {
       const __nv_bfloat16* xa = Xsm + (size_t)(mt * 16 + r) * KLP + c * 8;
       const __nv_bfloat16* wa = Wsm + (size_t)r * KLP + c * 8;
       const __nv_bfloat16* sa = Ssm + c * 8;
-#pragma unroll 4
+      // NOT unrolled: every CTA runs this kernel's code exactly once, so each distinct instruction line is a cold
+      // instruction-cache miss (measured: ~25 cycles per executed instruction in straight-line code); a compact loop
+      // body pays that once and then runs from L0
+#pragma unroll 1
       for (int kb = ks * kb_per; kb < (ks + 1) * kb_per; ++kb) {
         // one 16-byte load = 8 consecutive k of one row; the k → fragment-slot assignment is a permutation applied
         // identically to both operands (dot products do not care), so no ldmatrix / transposes are needed
@@ -207,72 +231,96 @@ decode_linear_kernel(DlParams p) {
     }
   }
   if (p.trace && blockIdx.x == 0 && lane == 0) p.trace[8 + warp] = clock64();      // per-warp end of MMA
-  // ---- 4. k reduction across the cluster + epilogue: every CTA finishes a 1/ksplit share of the [B x Nc] outputs
+  // ---- 4. k reduction + epilogue.  First every CTA folds its own k sub-slices into slice 0 (all threads), then the
+  //         cluster barrier, then every CTA finishes a 1/ksplit share of the [B x Nc] outputs, reading the other
+  //         CTAs' slice 0 over DSMEM (loads batched four ranks at a time: a DSMEM load is ~250 cycles).
+  __syncthreads();
+  if (p.ksub > 1) {
+    const int n4 = p.B * (Nc / 4);
+#pragma unroll 1
+    for (int i = tid; i < n4; i += DL_THREADS) {
+      float4 a = *reinterpret_cast<const float4*>(Asm + (size_t)i * 4);
+#pragma unroll 1
+      for (int ks = 1; ks < p.ksub; ++ks) {
+        const float4 q4 = *reinterpret_cast<const float4*>(Asm + ((size_t)ks * p.Bp * Nc) + (size_t)i * 4);
+        a.x += q4.x; a.y += q4.y; a.z += q4.z; a.w += q4.w;
+      }
+      *reinterpret_cast<float4*>(Asm + (size_t)i * 4) = a;
+    }
+  }
   if (p.ksplit > 1) dl_cluster_sync(); else __syncthreads();
   DL_STAMP(5);
   {
-    constexpr int GPR = Nc / 8;                    // 8-column groups per row
-    const int groups = p.B * GPR;
+    // ONE output element per thread and a rolled loop: this kernel is instruction-fetch bound (cold code runs at
+    // ~10-25 cycles per instruction; an epilogue unrolled over 8 elements per thread cost 2.6 k cycles), so the work is
+    // spread over as many threads as possible and every thread executes as few distinct instructions as possible.
+    // Element e = b * Nc + n; the CTAs of a cluster interleave rows of 32 consecutive elements.
+    if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[34] = clock64();        // epilogue loop entered
+    // Four consecutive outputs per thread (one 16-byte DSMEM / shared load per partial sum: scalar remote loads were
+    // transaction-bound at batch 64), warps of a cluster's CTAs interleaved; group gi covers elements 4·gi .. 4·gi+3
+    // of the row-major [B x Nc] tile.
+    const int total4 = p.B * (Nc / 4);
     const float inv_k = 1.0f / (float)p.K;
     const uint32_t asm_addr = dl_smem_u32(Asm);
-    for (int g = ks_cta + p.ksplit * tid; g < groups; g += p.ksplit * DL_THREADS) {
-      const int b = g / GPR, cg = g - b * GPR;
-      const int col = n0 + cg * 8;
-      if (col >= p.N) continue;
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      for (int ks = 0; ks < p.ksub; ++ks) {        // this CTA's k sub-slices
-        const float* ap = Asm + ((size_t)ks * p.Bp + b) * Nc + cg * 8;
-        const float4 lo = *reinterpret_cast<const float4*>(ap), hi = *reinterpret_cast<const float4*>(ap + 4);
-        v[0] += lo.x; v[1] += lo.y; v[2] += lo.z; v[3] += lo.w; v[4] += hi.x; v[5] += hi.y; v[6] += hi.z; v[7] += hi.w;
+    const int lane_e = tid & 31;
+    constexpr int G4R = Nc / 4;                    // groups per batch row
+#pragma unroll 1
+    for (int g0 = ((tid >> 5) * p.ksplit + ks_cta) * 32; g0 < total4; g0 += (DL_THREADS / 32) * p.ksplit * 32) {
+      const int gi = g0 + lane_e;                  // (no early exits: the row-sum below shuffles across the warp)
+      const int b = gi / G4R, n = (gi - b * G4R) * 4;
+      const int col = n0 + n;
+      const bool ok = gi < total4 && col < p.N;
+      const uint32_t off = (uint32_t)(ok ? gi : 0) * 16u;
+      float4 v4 = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(Asm) + off);
+#pragma unroll 1
+      for (int q = 1; q < p.ksplit; ++q) {         // the other CTAs' partial sums (slice 0 after the local fold)
+        const float4 r = dl_ld_cluster_f4(asm_addr + off, (uint32_t)((ks_cta + q) % p.ksplit));
+        v4.x += r.x; v4.y += r.y; v4.z += r.z; v4.w += r.w;
       }
-      for (int q = 1; q < p.ksplit; ++q) {         // partial sums of the other CTAs' k-slices, over DSMEM
-        const uint32_t rank = (uint32_t)((ks_cta + q) % p.ksplit);
-        for (int ks = 0; ks < p.ksub; ++ks) {
-          const uint32_t off = asm_addr + (uint32_t)((((size_t)ks * p.Bp + b) * Nc + cg * 8) * 4);
-          const float4 lo = dl_ld_cluster_f4(off, rank), hi = dl_ld_cluster_f4(off + 16, rank);
-          v[0] += lo.x; v[1] += lo.y; v[2] += lo.z; v[3] += lo.w; v[4] += hi.x; v[5] += hi.y; v[6] += hi.z; v[7] += hi.w;
-        }
-      }
-      const float rs = p.norm_scale ? rsqrtf(p.x_ss[b] * inv_k + p.norm_eps) : 1.0f;
-      const bool full = col + 8 <= p.N;
+      if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[32] = clock64();      // after the partial-sum reads
       float ss = 0.f;
+      if (ok) {
+        float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        const float rs = p.norm_scale ? rsqrtf(p.x_ss[b] * inv_k + p.norm_eps) : 1.0f;
+        const int nj = min(4, p.N - col);
+        __nv_bfloat16 qv[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = v[j] * rs;
-        if (p.bias && (full || col + j < p.N)) t += p.bias[col + j];
-        if (p.act == VG_ACT_RELU) t = fmaxf(t, 0.f);
-        else if (p.act == VG_ACT_GELU) t = gelu_f(t);
-        else if (p.act == VG_ACT_SILU) t = silu_f(t);
-        if (p.residual && (full || col + j < p.N)) t += __bfloat162float(p.residual[(int64_t)b * p.ld_res + col + j]);
-        v[j] = t;
-      }
-      if (p.y) {
-        __nv_bfloat16* yp = p.y + (int64_t)b * p.ldy + col;
-        if (full && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
-          uint4 pk;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            const float2 f = __bfloat1622float2(h[j]);
-            ss += f.x * f.x + f.y * f.y;
+        for (int j = 0; j < 4; ++j) {
+          float t = v[j] * rs;
+          if (j < nj) {
+            if (p.bias) t += p.bias[col + j];
+            if (p.act != VG_ACT_NONE) t = apply_act(t, p.act);
+            if (p.residual) t += __bfloat162float(p.residual[(int64_t)b * p.ld_res + col + j]);
           }
-          *reinterpret_cast<uint4*>(yp) = pk;
-        } else {
-          for (int j = 0; j < 8 && col + j < p.N; ++j) {
-            const __nv_bfloat16 qv = __float2bfloat16_rn(v[j]);
-            yp[j] = qv;
-            const float f = __bfloat162float(qv);
-            ss += f * f;
-          }
+          v[j] = t;
+          qv[j] = __float2bfloat16_rn(t);
+          const float f = __bfloat162float(qv[j]);
+          if (j < nj) ss = fmaf(f, f, ss);
         }
-        if (p.y_ss) atomicAdd(p.y_ss + b, ss);
+        if (p.y) {
+          __nv_bfloat16* yp = p.y + (int64_t)b * p.ldy + col;
+          if (nj == 4 && ((reinterpret_cast<uintptr_t>(yp) & 7) == 0)) {
+            *reinterpret_cast<uint2*>(yp) = *reinterpret_cast<const uint2*>(qv);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < nj) yp[j] = qv[j];
+          }
+        } else {
+          ss = 0.f;
+        }
+        if (p.y_f32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nj) p.y_f32[(int64_t)b * p.ldy32 + col + j] = v[j];
+        }
       }
-      if (p.y_f32) {
-        float* fp = p.y_f32 + (int64_t)b * p.ldy32 + col;
-        for (int j = 0; j < 8 && col + j < p.N; ++j) fp[j] = v[j];
+      if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[33] = clock64();      // after bias / activation / residual
+      if (p.y_ss && p.y) {
+        // lanes of a warp cover 128 consecutive elements: whole rows when Nc <= 128 divides 128 (always: Nc is a
+        // power of two <= 64), i.e. 128 / Nc rows per warp → segmented sum over G4R consecutive lanes
+        for (int o = 1; o < G4R && o < 32; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if ((lane_e & (G4R - 1)) == 0 && ok) atomicAdd(p.y_ss + b, ss);
       }
     }
   }

@@ -96,9 +96,9 @@ class LVTR(nn.Module):
         self.compute_dtype = torch.float32
         self.overlap_decoder = True         # diffusion decoder branch on a side stream (parallel graph branch)
         self.use_decode_engine = True       # bf16 single-frame steps run on decode.DecodeEngine ...
-        # ... up to this batch: measured on B200 (profiles/r01_decode.md) the weight-streaming engine wins below ~48
-        # sequences (0.57 vs 1.21 ms per step at B=1), the tcgen05 layer-by-layer path above (2.0 vs 3.7 ms at B=256)
-        self.decode_engine_max_batch = 48
+        # ... up to this batch: measured on B200 (profiles/r01_decode.md) the weight-streaming engine wins up to ~100
+        # sequences (0.47 vs 1.21 ms per step at B=1, 1.02 vs 1.37 at 64), the tcgen05 layer-by-layer path above
+        self.decode_engine_max_batch = 96
 
     # ------------------------------------------------------------------ configuration
     def set_compute_dtype(self, dtype: torch.dtype) -> "LVTR":
