@@ -239,6 +239,70 @@ def diffusion_loss(sd, p, hp, mel_scaled, mask, cond, t, noise):
     return (_mask3(pred, mask) - target).abs().mean(-1).sum(-1).sum()
 
 
+def unet_predict(sd, p, hp, x_t, t, cond, mask):
+    """ConditionalBottleNeckUNet.forward (unet.py:67-93): noise prediction for x_t at integer steps t [B]."""
+    te = hp["cond_unet"]["time_embedding"]
+    act = _ACT[te["activation"]["identifier"]]
+    emb = sincos_table(te["maxpos"], te["dim"], x_t.device)[t]
+    temb = _lin(sd, p + ".model.time_embedding.lin2", act(_lin(sd, p + ".model.time_embedding.lin1", emb)))
+    c = _mask3(_lin(sd, p + ".model.cond_net", cond), mask)
+    return _mask3(bottleneck_resnet(sd, p + ".model.unet", hp["cond_unet"]["unet"], x_t, mask, cond=c, temb=temb), mask)
+
+
+def cosine_alphas_cumprod(timesteps: int, s: float = 0.008) -> torch.Tensor:
+    """cosine_beta_schedule + cumprod (ddpm.py:127-138,171-180), float64 → float32 like the reference buffers."""
+    x = torch.linspace(0, timesteps, timesteps + 1, dtype=torch.float64)
+    ac = torch.cos(((x / timesteps) + s) / (1 + s) * math.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
+    return torch.cumprod(1.0 - betas, dim=0).float()
+
+
+def lvtr_decode(sd, hp, frames, mask, u_c, start, step_noise, sampling_steps):
+    """LVTR.decode (lvtr.py:288-306) → GaussianDiffusion1D.ddim_sample (ddpm.py:284-321), pred_noise objective.
+    ``start`` [B,T,n_mels] is the initial noise (torch.randn in the reference), ``step_noise`` the per-step
+    torch.randn_like draws (one per step except the last)."""
+    dh = hp["decoder"]["diffusion"]
+    assert dh.get("objective", "pred_noise") == "pred_noise" and dh["beta_schedule"]["identifier"] == "cosine"
+    T_total = dh["timesteps"]
+    eta, lo_hi, sig = dh.get("ddim_sampling_eta", 0.0), dh.get("clamp_range", [-1.0, 1.0]), dh.get("sigma", 1.0)
+    ac = cosine_alphas_cumprod(T_total).to(frames.device)
+    ids = frames[..., 0].long()
+    E = _mask3(F.embedding(ids, sd["token_embedding.weight"]), mask)
+    fused = E + F.relu(_lin(sd, "token_fuser.linear", frames[..., 1:]))                 # fuse_inputs :390-392
+    cond = _mask3(torch.cat([fused, u_c[:, None].expand(-1, fused.shape[1], -1)], -1), mask)
+    times = list(reversed(torch.linspace(-1, T_total - 1, steps=sampling_steps + 1).int().tolist()))
+    img = _mask3(start, mask)
+    noises = list(step_noise)
+    for t, t_next in zip(times[:-1], times[1:]):
+        tc = torch.full((frames.shape[0],), t, dtype=torch.long, device=frames.device)
+        eps_hat = unet_predict(sd, "decoder", hp["decoder"], img, tc, cond, mask)
+        x0 = (1.0 / ac[t]).sqrt() * img - (1.0 / ac[t] - 1).sqrt() * eps_hat      # predict_start_from_noise
+        x0 = _mask3(_mask3(x0, mask).clamp(lo_hi[0], lo_hi[1]), mask)
+        if t_next < 0:
+            img = x0
+            continue
+        a, a_next = ac[t], ac[t_next]
+        sigma = eta * ((1 - a / a_next) * (1 - a_next) / (1 - a)).sqrt()
+        c = (1 - a_next - sigma ** 2).sqrt()
+        img = _mask3(x0 * a_next.sqrt() + c * eps_hat + sigma * noises.pop(0) * sig, mask)
+    return img * dh.get("input_scale", 1.0)
+
+
+def lvtr_likelihood(sd, hp, x, mask, init_state):
+    """LVTR.likelihood (lvtr.py:337-388) with the temperature-0 posterior: per-utterance mean token log-probability."""
+    ids = x[..., 0].long()
+    mel = x[..., 1:]
+    E = _mask3(F.embedding(ids, sd["token_embedding.weight"]), mask)
+    q = _lin(sd, "encoder.1.mean", bottleneck_resnet(sd, "encoder.0", hp["encoder"], mel, mask))   # sample = mean
+    fused = E + F.relu(_lin(sd, "token_fuser.linear", q))
+    shifted = _mask3(torch.cat([init_state, fused], 1)[:, :-1], mask)
+    H, _ = transformer_stack(sd, "transformer.0", hp["transformer"], shifted, mask)
+    logits = _lin(sd, "token_predictor.linear", F.relu(_lin(sd, "token_spliter.linear", H)))
+    lp = torch.log_softmax(logits, -1).gather(-1, ids[..., None])[..., 0]
+    return torch.where(mask, lp, torch.zeros_like(lp)).sum(-1) / mask.sum(-1)
+
+
 # ------------------------------------------------------------------------------------- the model
 def lvtr_forward(sd: Dict[str, torch.Tensor], hp: dict, x: torch.Tensor, mask: torch.Tensor,
                  utterance: torch.Tensor, utt_mask: torch.Tensor, rng: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

@@ -156,7 +156,30 @@ def main():
             state = o["output"][:, -1:]
     dec["final_kv_key0"] = kv[0]["key"].clone()
 
-    fixture = {"config": cfg, "n_mels": n_mels, "state_dict": sd,
+    # ---------------- diffusion decoding of generated frames (lvtr.py:288-306 → ddpm.py:284-321), DDIM with 6
+    # sampling steps; the start noise (torch.randn) and the per-step noises (torch.randn_like) are injected
+    nsamp = 6
+    model.decoder.sampling_timesteps = nsamp
+    frames = torch.cat([tokens[..., None].float(), torch.randn(B, T, 4, generator=g)], -1)
+    start = torch.randn(B, T, n_mels, generator=g)
+    step_noise = [torch.randn(B, T, n_mels, generator=g) for _ in range(nsamp - 1)]
+    saved_randn = torch.randn
+    torch.randn = lambda *a, **k: start.clone()
+    try:
+        with torch.no_grad(), PatchedRNG(randn_like=step_noise, rand=[], randint=[]):
+            mel_out = model.decode(TensorMask(frames, mask), u_c=out["u_c"].detach())
+    finally:
+        torch.randn = saved_randn
+    ddim = {"frames": frames, "u_c": out["u_c"].detach().clone(), "start": start, "noise": step_noise,
+            "steps": nsamp, "output": mel_out.value.detach().clone()}
+
+    # ---------------- likelihood scoring (lvtr.py:337-388), temperature-0 posterior, injected BOS state
+    s0l = torch.rand(B, 1, 64, generator=g) * 2 - 1
+    with torch.no_grad(), PatchedRNG(randn_like=[rng["eps_q"], rng["eps_p"]], rand=[(s0l + 1) / 2], randint=[]):
+        ll = model.likelihood(TensorMask(x, mask), temperature=0.0)
+    like = {"init_state": s0l, "value": ll.detach().clone()}
+
+    fixture = {"config": cfg, "n_mels": n_mels, "state_dict": sd, "ddim": ddim, "likelihood": like,
                "inputs": {"x": x, "mask": mask, "utterance": utt, "utt_mask": utt_mask, **rng},
                "forward": fwd, "grads": grads, "decode": dec,
                "note": "generated by tests/golden/make_golden.py from the unmodified reference (torch %s)" % torch.__version__}

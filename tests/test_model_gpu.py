@@ -215,6 +215,29 @@ def test_train_step_overlapped_graph_matches_serial_eager(golden):
     assert max_rel(p1, p0) < 1e-2
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 6e-2)])
+def test_ddim_decode_matches_reference(golden, dtype, tol):
+    """LVTR.decode (DDIM, 6 steps) against the real reference's output with the same injected noises; every
+    UNet pass runs on the dwconv_ln / tcgen05-or-SIMT GEMM kernels."""
+    d, i = golden["ddim"], golden["inputs"]
+    model = build_small(golden, dtype).eval()
+    model.decoder.sampling_timesteps = d["steps"]
+    out = model.decode(TensorMask(d["frames"].to(DEV), i["mask"].to(DEV)), u_c=d["u_c"].to(DEV),
+                       start_noise=d["start"], step_noise=[n.to(DEV) for n in d["noise"]])
+    assert max_rel(out.value.cpu(), d["output"]) < tol
+    assert float(out.value[~i["mask"].to(DEV)].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_likelihood_matches_reference(golden, dtype, tol):
+    """LVTR.likelihood (temperature-0 posterior, per-utterance mean token log-probability)."""
+    i, l = golden["inputs"], golden["likelihood"]
+    model = build_small(golden, dtype).eval()
+    val = model.likelihood(TensorMask(i["x"].to(DEV), i["mask"].to(DEV)), temperature=0.0,
+                           init_state=l["init_state"].to(DEV))
+    assert max_rel(val.cpu(), l["value"]) < tol
+
+
 # ------------------------------------------------------------------------- fused latent kernels vs oracle
 def test_latent_kernels_against_oracle(golden):
     sd = {k: v.to(DEV) for k, v in golden["state_dict"].items()}

@@ -58,3 +58,19 @@ def test_cached_decode_matches_reference(golden):
         kv = o["kv"]
         state = o["output"][:, -1:]
     torch.testing.assert_close(kv[0]["key"], d["final_kv_key0"], **TOL)
+
+
+def test_ddim_decode_matches_reference(golden):
+    """LVTR.decode → ddim_sample (lvtr.py:288-306, ddpm.py:284-321), 6 sampling steps, injected noises."""
+    d, i = golden["ddim"], golden["inputs"]
+    out = O.lvtr_decode(golden["state_dict"], golden["config"], d["frames"], i["mask"], d["u_c"], d["start"], d["noise"],
+                        d["steps"])
+    torch.testing.assert_close(out, d["output"], rtol=1e-4, atol=1e-4)
+    assert float(out[~i["mask"]].abs().max()) == 0.0
+
+
+def test_likelihood_matches_reference(golden):
+    """LVTR.likelihood (lvtr.py:337-388), temperature-0 posterior."""
+    i, l = golden["inputs"], golden["likelihood"]
+    val = O.lvtr_likelihood(golden["state_dict"], golden["config"], i["x"], i["mask"], l["init_state"])
+    torch.testing.assert_close(val, l["value"], rtol=2e-5, atol=2e-5)

@@ -335,10 +335,14 @@ class LVTR(nn.Module):
 
     # ------------------------------------------------------------------ auxiliary entry points
     @torch.no_grad()
-    def decode(self, x: TensorMask, c: Optional[TensorMask] = None, u_c: Optional[torch.Tensor] = None) -> TensorMask:
-        """diffusion sampling of mel frames from (token, z) frames (lvtr.py:288-306; torch loop)."""
+    def decode(self, x: TensorMask, c: Optional[TensorMask] = None, u_c: Optional[torch.Tensor] = None, *,
+               start_noise: Optional[torch.Tensor] = None, step_noise=None) -> TensorMask:
+        """diffusion sampling of mel frames from (token, z) frames (lvtr.py:288-306): the sampling loop
+        is host code, every UNet pass runs on the libvgslm conv / GEMM kernels.  ``start_noise`` / ``step_noise``
+        inject the reference's torch.randn / torch.randn_like draws (additive API, parity tests)."""
         n_frames = int(x.value.size(1) * (1.0 / self.sample_ratio))
-        noise = torch.randn(x.value.size(0), n_frames, self.input_dim, device=x.device)
+        noise = (start_noise.to(x.value.device) if start_noise is not None
+                 else torch.randn(x.value.size(0), n_frames, self.input_dim, device=x.device))
         noise = TensorMask.fromlength(noise, TensorMask.resize_length(x.length, 1.0 / self.sample_ratio)).apply_mask()
         if self.use_tokens:
             tokens_id, x = x.split(1)
@@ -347,7 +351,7 @@ class LVTR(nn.Module):
         if u_c is not None:
             x = x.cat(u_c[:, None].expand(-1, x.value.size(1), -1).to(x.value.dtype))
         with self._autocast():
-            return self.decoder.sample(noise, x.apply_mask()) * self.diff_scaling
+            return self.decoder.sample(noise, x.apply_mask(), step_noise=step_noise) * self.diff_scaling
 
     @torch.no_grad()
     def encode(self, x: TensorMask, temperature: float = 1.0, beta: Optional[torch.Tensor] = None,

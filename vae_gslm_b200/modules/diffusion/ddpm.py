@@ -159,8 +159,11 @@ class GaussianDiffusion1D(nn.Module):
         return img
 
     @torch.no_grad()
-    def ddim_sample(self, start: TensorMask, cond: TensorMask, **kwargs) -> TensorMask:
+    def ddim_sample(self, start: TensorMask, cond: TensorMask, step_noise=None, **kwargs) -> TensorMask:
+        """``step_noise``: optional list of the per-step torch.randn_like draws (one per step but the last) — additive
+        API for parity tests; the reference draws them inside the loop (ddpm.py:312)."""
         batch, device = start.value.shape[0], self.betas.device
+        step_noise = list(step_noise) if step_noise is not None else None
         times = torch.linspace(-1, self.num_timesteps - 1, steps=self.sampling_timesteps + 1)
         times = list(reversed(times.int().tolist()))
         img = start
@@ -175,10 +178,13 @@ class GaussianDiffusion1D(nn.Module):
             a, a_next = self.alphas_cumprod[time], self.alphas_cumprod[time_next]
             sigma = self.ddim_sampling_eta * ((1 - a / a_next) * (1 - a_next) / (1 - a)).sqrt()
             c = (1 - a_next - sigma ** 2).sqrt()
-            noise = torch.randn_like(img.value) * self.sigma
+            noise = (step_noise.pop(0).to(img.value) if step_noise is not None else torch.randn_like(img.value)) * self.sigma
             img = TensorMask(x0.value * a_next.sqrt() + c * pred_noise.value + sigma * noise, x0.mask).apply_mask()
         return img
 
     @torch.no_grad()
-    def sample(self, start: TensorMask, cond: TensorMask, **kwargs) -> TensorMask:
-        return (self.ddim_sample if self.is_ddim_sampling else self.p_sample_loop)(start, cond, **kwargs)
+    def sample(self, start: TensorMask, cond: TensorMask, step_noise=None, **kwargs) -> TensorMask:
+        if self.is_ddim_sampling:
+            return self.ddim_sample(start, cond, step_noise=step_noise, **kwargs)
+        assert step_noise is None, "noise injection is implemented for the DDIM sampler"
+        return self.p_sample_loop(start, cond, **kwargs)
