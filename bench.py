@@ -280,7 +280,36 @@ def decode_bench(model, dev, peaks, batches=(1, 64, 256), prompt=150, steps=48):
                         "path": "decode engine (vg_decode_linear)" if (model.use_decode_engine and
                                                                        B <= model.decode_engine_max_batch)
                         else "layer-by-layer (tcgen05 GEMM)"}
+    out["ddim_decode"] = ddim_bench(model, dev)
     return out
+
+
+def ddim_bench(model, dev, B=16, T=650, steps=100, eta=0.5):
+    """diffusion decoding of generated frames (configs/infer: 100 DDIM steps, eta 0.5, 3 s + 10 s = 650
+    frames), whole loop replayed from one CUDA graph; mel frames per second."""
+    from vae_gslm_b200.trainers.speech.sampler import GraphedDecode
+    g = torch.Generator().manual_seed(11)
+    frames = torch.cat([torch.randint(0, VOCAB, (B, T, 1), generator=g).float(), torch.randn(B, T, 4, generator=g)], -1).to(dev)
+    mask = torch.ones(B, T, dtype=torch.bool, device=dev)
+    u_c = torch.randn(B, 128, generator=g).to(dev)
+    dec = model.decoder
+    saved = (dec.sampling_timesteps, dec.ddim_sampling_eta)
+    dec.sampling_timesteps, dec.ddim_sampling_eta = steps, eta
+    try:
+        graphed = GraphedDecode(model, frames, mask, u_c)
+        graphed()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            graphed()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+    finally:
+        dec.sampling_timesteps, dec.ddim_sampling_eta = saved
+    return {"mel_frames_per_sec": round(B * T / (ms / 1e3), 1), "ms": round(ms, 2), "batch": B, "frames": T,
+            "ddim_steps": steps, "mode": "whole DDIM loop replayed from one CUDA graph"}
 
 
 # ====================================================================================== CPU baseline / reference arm

@@ -426,3 +426,23 @@ def test_cuda_graph_decode_matches_eager(golden):
     # identical tokens; latents equal up to the split-KV summation order (the graph freezes the split count)
     assert torch.equal(runs[0][..., 0], runs[1][..., 0])
     assert max_rel(runs[1][..., 1:], runs[0][..., 1:]) < 1e-5
+
+
+def test_graphed_ddim_decode_matches_eager(golden):
+    """the CUDA-graphed diffusion decode (trainers/speech/sampler.py:GraphedDecode) with eta = 0 (no noise draws)
+    reproduces the eager loop."""
+    from vae_gslm_b200.trainers.speech.sampler import GraphedDecode
+    d, i = golden["ddim"], golden["inputs"]
+    model = build_small(golden, torch.bfloat16).eval()
+    model.decoder.sampling_timesteps, model.decoder.ddim_sampling_eta = 5, 0.0
+    frames, mask, u_c = d["frames"].to(DEV), i["mask"].to(DEV), d["u_c"].to(DEV)
+    torch.manual_seed(3)
+    start = torch.randn(frames.shape[0], frames.shape[1], golden["n_mels"], device=DEV)
+    eager = model.decode(TensorMask(frames, mask), u_c=u_c, start_noise=start).value
+    saved = torch.randn
+    torch.randn = lambda *a, **k: start.clone()          # the graph's start noise = the eager one
+    try:
+        graphed = GraphedDecode(model, frames, mask, u_c)
+    finally:
+        torch.randn = saved
+    assert max_rel(graphed(), eager) < 1e-5

@@ -49,6 +49,39 @@ class GraphedStep:
         return self.state
 
 
+class GraphedDecode:
+    """``LVTR.decode`` (DDIM sampling of mel frames, lvtr.py:288-306 → ddpm.py:284-321) captured into ONE CUDA graph.
+
+    The sampling schedule is fixed by the configuration, so the whole loop — ``sampling_timesteps`` UNet passes of ~60
+    short kernels each — is unrolled into the graph; time steps and DDIM coefficients are baked in, the noise draws are
+    graph-safe torch RNG calls.  ``frames`` [B,T,1+L], ``mask`` [B,T] and ``u_c`` [B,E] are static input buffers."""
+
+    def __init__(self, model: nn.Module, frames: torch.Tensor, mask: torch.Tensor, u_c: Optional[torch.Tensor]) -> None:
+        self.model = model
+        self.frames, self.mask = frames.clone(), mask.clone()
+        self.u_c = u_c.clone() if u_c is not None else None
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            model.decode(TensorMask(self.frames, self.mask), u_c=self.u_c)          # warm-up (lazy initialisations)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.out = model.decode(TensorMask(self.frames, self.mask), u_c=self.u_c).value
+
+    def __call__(self, frames: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+                 u_c: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if frames is not None:
+            self.frames.copy_(frames)
+        if mask is not None:
+            self.mask.copy_(mask)
+        if u_c is not None and self.u_c is not None:
+            self.u_c.copy_(u_c)
+        self.graph.replay()
+        return self.out
+
+
 class ARTRSampler(object):
     def __init__(self, model: nn.Module, use_cuda_graph: bool = True):
         self.model = model
