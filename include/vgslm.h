@@ -142,6 +142,8 @@ int vg_attn_decode(const void* qkv /* [B, 3*H*D] */, void* k_cache, void* v_cach
                    int64_t B, int64_t H, int64_t D, int64_t Tmax, int64_t pos,
                    const int32_t* pos_dev /* nullable: device-resident position (CUDA-graph replay) */,
                    int64_t splits, float scale, int dtype, void* workspace, size_t workspace_bytes,
+                   int32_t* tickets /* nullable: [B*H] counters, zero on entry and left zero → the split-KV partials are
+                                       merged by the last CTA of each (b,h) in the SAME launch (no merge kernel) */,
                    vg_stream_t stream);
 /* *counter += delta (device-side step counter used with pos_dev) */
 int vg_add_i32(int32_t* counter, int32_t delta, vg_stream_t stream);

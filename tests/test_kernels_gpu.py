@@ -328,11 +328,13 @@ def test_attention_decode_and_cache(dtype):
     assert rel_err(o0, _attn_ref(qkv0, H, None, slopes)) < tol(dtype)
     k_all, v_all = qkv0[..., C:2 * C].clone(), qkv0[..., 2 * C:].clone()
     pos = 17
+    tickets = torch.zeros(B * H, dtype=torch.int32, device=DEV)      # in-kernel merge of the split-KV partials
     for step in range(5):
         qkv = (0.5 * torch.randn(B, 1, 3 * C, device=DEV)).to(dtype)
-        for splits in (1, 3):
+        for splits, tk in ((1, None), (3, None), (3, tickets), (5, tickets)):
             kc2, vc2 = kc.clone(), vc.clone()
-            o = ops.attention_decode(qkv.view(B, 3 * C), kc2, vc2, pos, slopes, splits=splits)
+            o = ops.attention_decode(qkv.view(B, 3 * C), kc2, vc2, pos, slopes, splits=splits, tickets=tk)
+            assert int(tickets.abs().sum()) == 0
             k_ref = torch.cat([k_all, qkv[..., C:2 * C]], 1)
             v_ref = torch.cat([v_all, qkv[..., 2 * C:]], 1)
             ref = _attn_ref(qkv, H, None, slopes, q_offset=pos, k=k_ref, v=v_ref)

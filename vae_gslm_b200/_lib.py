@@ -129,7 +129,7 @@ _SIGNATURES = {
                               _i64, _i64, _i64, _i64, _i64, _i64, _f32, C.c_int, _p, _sz, _p]),
     "vg_attn_decode_workspace": (_sz, [_i64, _i64, _i64, _i64]),
     "vg_attn_decode": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _f32, C.c_int,
-                                 _p, _sz, _p]),
+                                 _p, _sz, _p, _p]),
     "vg_add_i32": (C.c_int, [_p, _i32, _p]),
     "vg_decode_linear_workspace": (_sz, [_i64, _i64]),
     "vg_decode_linear": (C.c_int, [C.POINTER(DecodeLinearArgs), _p, _sz, _p]),

@@ -19,8 +19,10 @@ template <typename T>
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __restrict__ v_cache,
                    T* __restrict__ out, float* __restrict__ partial, const float* __restrict__ slopes,
-                   int H, int Tmax, int pos_arg, const int32_t* __restrict__ pos_dev, int splits, float scale) {
+                   int H, int Tmax, int pos_arg, const int32_t* __restrict__ pos_dev, int splits, float scale,
+                   int* __restrict__ tickets) {
   __shared__ float sm_m[DEC_GROUPS], sm_l[DEC_GROUPS];
+  __shared__ int s_last;
   // programmatic dependent launch: the weight-streaming GEMM that follows (decode_linear.cu) may start prefetching its
   // weight slab now; it still waits (griddepcontrol.wait) for this grid to finish before it reads our output
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -113,6 +115,32 @@ attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __rest
       if (d == 0) { pp[0] = M; pp[1] = L; }
     }
   }
+  if (splits > 1 && tickets) {
+    // merge in the same launch: the last CTA of this (b, h) to finish combines the split partials (a separate merge
+    // kernel costs a kernel boundary per layer of a ~0.5 ms step).  tickets[b·H+h] is zero on entry and left zero.
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(tickets + (int64_t)b * H + h, 1) == splits - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (threadIdx.x < DD) {
+        const int d = threadIdx.x;
+        const float* pp = partial + ((int64_t)b * H + h) * splits * (DD + 2);
+        float M = -CUDART_INF_F;
+        for (int s2 = 0; s2 < splits; ++s2) M = fmaxf(M, __ldcg(pp + s2 * (DD + 2)));
+        float L = 0.f, O = 0.f;
+        for (int s2 = 0; s2 < splits; ++s2) {
+          const float ms = __ldcg(pp + s2 * (DD + 2));
+          const float w = (ms == -CUDART_INF_F) ? 0.f : expf(ms - M);
+          L += __ldcg(pp + s2 * (DD + 2) + 1) * w;
+          O += __ldcg(pp + s2 * (DD + 2) + 2 + d) * w;
+        }
+        out[((int64_t)b * H + h) * DD + d] = from_f32<T>(L > 0.f ? O / L : 0.f);
+      }
+      if (threadIdx.x == 0) tickets[(int64_t)b * H + h] = 0;
+    }
+  }
 }
 
 template <typename T>
@@ -160,7 +188,7 @@ extern "C" size_t vg_attn_decode_workspace(int64_t B, int64_t H, int64_t D, int6
 extern "C" int vg_attn_decode(const void* qkv, void* k_cache, void* v_cache, void* out, const float* slopes,
                               int64_t B, int64_t H, int64_t D, int64_t Tmax, int64_t pos, const int32_t* pos_dev,
                               int64_t splits, float scale, int dtype, void* workspace, size_t workspace_bytes,
-                              vg_stream_t stream) {
+                              int32_t* tickets, vg_stream_t stream) {
   VG_REQUIRE(qkv && k_cache && v_cache && out, -1, "vg_attn_decode: null pointer");
   VG_REQUIRE(valid_dtype(dtype), -2, "vg_attn_decode: bad dtype");
   VG_REQUIRE(D == DD, -3, "vg_attn_decode: head dim %lld unsupported (only 64)", (long long)D);
@@ -176,14 +204,14 @@ extern "C" int vg_attn_decode(const void* qkv, void* k_cache, void* v_cache, voi
   if (dtype == VG_F32) {
     attn_decode_kernel<float><<<grid, DEC_WARPS * 32, 0, st>>>((const float*)qkv, (float*)k_cache, (float*)v_cache,
                                                               (float*)out, (float*)workspace, slopes, (int)H,
-                                                              (int)Tmax, (int)pos, pos_dev, (int)splits, scale);
+                                                              (int)Tmax, (int)pos, pos_dev, (int)splits, scale, tickets);
   } else {
     attn_decode_kernel<__nv_bfloat16><<<grid, DEC_WARPS * 32, 0, st>>>(
         (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, (__nv_bfloat16*)out,
-        (float*)workspace, slopes, (int)H, (int)Tmax, (int)pos, pos_dev, (int)splits, scale);
+        (float*)workspace, slopes, (int)H, (int)Tmax, (int)pos, pos_dev, (int)splits, scale, tickets);
   }
   VG_LAUNCH_CHECK("vg_attn_decode");
-  if (splits > 1) {
+  if (splits > 1 && !tickets) {
     dim3 g2((unsigned)H, (unsigned)B);
     if (dtype == VG_F32)
       attn_decode_merge_kernel<float><<<g2, DD, 0, st>>>((const float*)workspace, (float*)out, (int)H, (int)splits);

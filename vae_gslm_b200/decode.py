@@ -68,6 +68,7 @@ class DecodeEngine:
         self.ws = ops.decode_linear_workspace(B, max(3 * d, ffd, self.w_split.shape[0], self.w_head.shape[0],
                                                        self.w_tok.shape[0]), device)
         self.slopes = stack.rpe.slopes if stack.rpe is not None else None
+        self.tickets = torch.zeros(B * self.nheads, dtype=torch.int32, device=device)    # in-kernel split-KV merge
 
     @torch.no_grad()
     def run(self, u: torch.Tensor, kv: List) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -86,7 +87,7 @@ class DecodeEngine:
             ops.decode_linear(self.x, lw["w_in"], ws, norm_scale=lw["n1"], x_ss=self.ss_a, norm_eps=lw["eps1"],
                               out=self.qkv, zero_ss=self.ss_b, overlap=ov)
             o = ops.attention_decode(self.qkv, cache.k(kv[i].index), cache.v(kv[i].index), pos, self.slopes,
-                                     cache.pos_dev, out=self.o)
+                                     cache.pos_dev, out=self.o, tickets=self.tickets)
             ops.decode_linear(o, lw["w_out"], ws, residual=self.x, out=self.x, y_ss=self.ss_b, overlap=ov)
             ops.decode_linear(self.x, lw["w1"], ws, norm_scale=lw["n3"], x_ss=self.ss_b, norm_eps=lw["eps3"],
                               bias=lw["b1"], act=lw["act"], out=self.h, zero_ss=self.ss_a, overlap=ov)

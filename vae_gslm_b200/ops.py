@@ -549,7 +549,7 @@ def kv_append(k: torch.Tensor, v: torch.Tensor, k_cache: torch.Tensor, v_cache: 
 def attention_decode(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, pos: int,
                      slopes: Optional[torch.Tensor], pos_dev: Optional[torch.Tensor] = None,
                      scale: Optional[float] = None, splits: Optional[int] = None,
-                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     out: Optional[torch.Tensor] = None, tickets: Optional[torch.Tensor] = None) -> torch.Tensor:
     """single-token step: append this token's k/v at ``pos`` and attend over cache rows [0, pos]."""
     B, C3 = qkv.shape
     _, H, Tmax, D = k_cache.shape
@@ -562,8 +562,11 @@ def attention_decode(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Te
         out = torch.empty((B, C3 // 3), dtype=qkv.dtype, device=qkv.device)
     assert out.shape == (B, C3 // 3) and out.is_contiguous() and out.dtype == qkv.dtype
     ws = L.workspace(L.load().vg_attn_decode_workspace(B, H, D, splits), qkv.device)
+    if tickets is not None:      # zero-initialised int32 [B*H] counters: split partials merged inside the same launch
+        assert tickets.dtype == torch.int32 and tickets.numel() >= B * H
     L.call("vg_attn_decode", L.ptr(qkv), L.ptr(k_cache), L.ptr(v_cache), L.ptr(out), L.ptr(slopes), B, H, D, Tmax,
-           pos, L.ptr(pos_dev), splits, float(scale), L.dtype_id(qkv.dtype), L.ptr(ws), ws.numel(), L.stream())
+           pos, L.ptr(pos_dev), splits, float(scale), L.dtype_id(qkv.dtype), L.ptr(ws), ws.numel(), L.ptr(tickets),
+           L.stream())
     return out
 
 
