@@ -124,6 +124,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # (Tried and rejected, profiles/r01_scaling.md: capping NCCL to 8 CTAs and the persistent GEMM grids to the other
+        #  140 SMs — NCCL_MAX_CTAS=8 VG_GEMM_SMS=140 — makes the all-reduce too slow to hide: 22.9 vs 21.2 ms at N=8.)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torchrun)"
     _lib.load()

@@ -93,6 +93,9 @@ typedef struct {
 size_t vg_gemm_workspace(const vg_gemm_args* a, int backend);
 int    vg_gemm(const vg_gemm_args* a, int backend, void* workspace, size_t workspace_bytes,
                vg_stream_t stream);
+/* SMs the persistent tcgen05 GEMM grids may occupy (default 148 = all; env VG_GEMM_SMS).  Data-parallel training leaves
+ * a few SMs to the NCCL all-reduce kernels that overlap backward (scripts/train.py:93-95 → DDP). */
+int    vg_set_gemm_sm_budget(int sms);
 /* column sums: out[n] = beta * out[n] + sum_m X[m,n] (bias gradients), deterministic; beta in {0,1}. */
 size_t vg_colsum_workspace(int64_t rows, int64_t cols);
 int    vg_colsum(const void* x, int64_t ld, float* out, int64_t rows, int64_t cols, int x_dtype, float beta,

@@ -82,6 +82,16 @@ bool gemm_tc_supported(const vg_gemm_args* a) {
 }
 
 
+static int g_sm_budget = 0;
+int gemm_sm_budget() {
+  if (g_sm_budget == 0) {
+    const char* e = getenv("VG_GEMM_SMS");
+    int v = e ? atoi(e) : kNumSMs;
+    g_sm_budget = (v >= 16 && v <= kNumSMs) ? (v & ~1) : kNumSMs;
+  }
+  return g_sm_budget;
+}
+
 // ---- tile / split-K selection -----------------------------------------------------------------------
 // A work unit is (128 x BN output tile, k-range).  Cost model in microseconds, fitted to per-shape sweeps on B200
 // (profiles/r01_gemm_splitk_sweep.md): one 64-deep k-block of a 128x256 tile costs ~0.50 us, of a 128x128 tile
@@ -116,7 +126,7 @@ static TcPlan pick_plan(const vg_gemm_args* a) {
       if (env_splits && can_split && s != env_splits) continue;
       const int64_t kbpu = ceil_div(num_kb, s);
       if (s > 1 && kbpu < 8) break;
-      const int64_t waves = ceil_div(tiles * s, kNumSMs);
+      const int64_t waves = ceil_div(tiles * s, gemm_sm_budget());
       const double cost = (double)waves * ((double)kbpu * per_kb + (s > 1 ? 2.5 : 0.0));
       if (cost < best_cost * 0.97) { best_cost = cost; best = TcPlan{bn, s, 0}; }   // ties → fewer splits / smaller BN
     }
@@ -172,3 +182,9 @@ int gemm_tc_launch(const vg_gemm_args* a, cudaStream_t st) {
 }
 
 }  // namespace vg
+
+extern "C" int vg_set_gemm_sm_budget(int sms) {
+  VG_REQUIRE(sms >= 16 && sms <= vg::kNumSMs, -3, "vg_set_gemm_sm_budget: %d not in [16, %d]", sms, vg::kNumSMs);
+  vg::g_sm_budget = sms & ~1;
+  return 0;
+}

@@ -277,6 +277,11 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpilogue& e, uint8_t* 
   }
 }
 
+// SMs the persistent GEMM grids may occupy (default: all 148).  Data-parallel runs leave a few SMs to the NCCL kernels
+// (VG_GEMM_SMS / vg_set_gemm_sm_budget): a persistent CTA whose SM is held by a long-running all-reduce kernel cannot
+// start, and with the static tile schedule its tiles wait with it.
+int gemm_sm_budget();
+
 // One work unit = (output tile, k-range).  With splits == 1 a unit is a whole tile.
 struct TcUnit {
   int m0, n0, kb0, kb1;
@@ -516,7 +521,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_ge
   // a variant this instantiation does not specialise falls back to the generic epilogue (TCV_RED has no generic
   // equivalent: the host only selects it where VMASK carries it)
   const int64_t units = ceil_div(a->M, TBM * CTAS) * ceil_div(a->N, BN) * epi.splits;
-  const int max_groups = kNumSMs / CTAS;
+  const int max_groups = gemm_sm_budget() / CTAS;
   const int grid = (int)(units < max_groups ? units : max_groups) * CTAS;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
