@@ -3,11 +3,12 @@
 Same constructor, sub-module names / state-dict keys and public methods as the reference ``LVTR``;
 ``forward`` and ``step`` run on the fused CUDA kernels of libvgslm:
 
-    conv encoder (torch/cuDNN) → latent_front kernel → stack-input GEMM → 16 × [RMSNorm, QKV GEMM,
-    attention, out-proj GEMM(+res+mask), RMSNorm, FFN1 GEMM(+bias+GELU), FFN2 GEMM(+bias+res+mask)]
+    conv encoder (dwconv_ln kernel + 1x1-conv GEMMs) → latent_front kernel → stack-input GEMM → 16 × [RMSNorm, QKV
+    GEMM, attention, out-proj GEMM(+res+mask), RMSNorm, FFN1 GEMM(+bias+GELU), FFN2 GEMM(+bias+res+mask)]
     → RMSNorm → one GEMM for q_spliter|token_spliter (+bias+ReLU) → one GEMM for prior mean|logstd|4×FiLM
-    → latent_back kernel (flow + log_p + KL) ; logit GEMM → softmax-CE kernel ; UNet (torch/cuDNN) between
-    the q_sample and masked-L1 kernels.
+    → latent_back kernel (flow + log_p + KL) ; logit GEMM → softmax-CE kernel ; diffusion UNet (same conv kernels)
+    between the q_sample and masked-L1 kernels, on a side stream concurrently with the transformer.
+    Single-frame cached steps (``step``) run on ``decode.DecodeEngine`` (weight-streaming ``vg_decode_linear``).
 
 Additive API: the five RNG draws of the reference forward can be injected
 (``eps_q, init_state, eps_p, diff_t, diff_noise``), ``step`` accepts ``eps=`` / ``token_u=`` /

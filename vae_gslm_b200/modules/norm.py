@@ -2,8 +2,9 @@
 
 ``RMSNorm`` runs the fused CUDA kernel (fp32 statistics, parameter named ``scale`` as in the
 checkpoint contract).  ``InstanceNorm`` — which in the reference is a per-time-step LayerNorm over the
-channel dimension of a B,C,T tensor (:35-47) — is only used by the conv encoder / UNet, which stay on
-torch/cuDNN this round.
+channel dimension of a B,C,T tensor (:35-47) — holds the parameters of the conv blocks' channel norm; in the
+residual blocks of the conv encoder / UNet it is evaluated inside the fused ``dwconv_ln`` kernel
+(``modules/conv/layers.py``), and as a torch module only by the small utterance encoder.
 """
 from typing import Optional
 
