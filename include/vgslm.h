@@ -186,6 +186,8 @@ size_t vg_decode_linear_workspace(int64_t max_batch, int64_t max_n);
 int    vg_decode_linear(const vg_decode_linear_args* a, void* workspace, size_t workspace_bytes, vg_stream_t stream);
 /* debug aid: when non-null, CTA 0 of every following vg_decode_linear launch writes 7 clock64 phase stamps to buf */
 int    vg_debug_decode_linear_trace(void* buf /* device, 48 x uint64, nullable */);
+/* debug: clock64 phase stamps of CTA (0,0,0) of the tcgen05 attention kernels, 8 per loop iteration (tools/attn_trace.py) */
+int    vg_debug_attn_trace(void* buf /* device, 256 x uint64, nullable */);
 
 /* ---- fused latent front end: lvtr.py:151-169 (+ linear/layers.py:87-134,150-152, lvtr.py:390-392)
  * per frame: mean/logstd heads (Linear L→L), z = (mean + exp(logstd)·eps·temperature)·mask,

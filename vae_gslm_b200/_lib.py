@@ -135,6 +135,7 @@ _SIGNATURES = {
     "vg_decode_linear_workspace": (_sz, [_i64, _i64]),
     "vg_decode_linear": (C.c_int, [C.POINTER(DecodeLinearArgs), _p, _sz, _p]),
     "vg_debug_decode_linear_trace": (C.c_int, [_p]),
+    "vg_debug_attn_trace": (C.c_int, [_p]),
     "vg_kv_append": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, C.c_int, _p]),
     "vg_latent_front_fwd": (C.c_int, [C.POINTER(LatentFrontArgs), _p]),
     "vg_latent_front_bwd_workspace": (_sz, [_i64, _i64, _i32, _i32, _i32]),

@@ -395,6 +395,7 @@ static int attn_bwd_launch(const void* dout, const void* q, const void* k, const
 }  // namespace vg
 
 namespace vg {
+void attn_tc_set_trace(void* buf);
 bool attn_tc_supported(int dtype, int64_t D, int64_t ld_q, int64_t ld_kv, const void* q, const void* k, const void* v,
                        int64_t kv_batch_stride, int64_t kv_head_stride);
 int attn_tc_fwd_launch(const void* q, const void* k, const void* v, int64_t ld_q, int64_t ld_kv, void* out,
@@ -409,6 +410,11 @@ static int g_attn_backend = 0;     // 0 = auto (tcgen05 for bf16), 1 = CUDA-core
 }  // namespace vg
 
 using namespace vg;
+
+extern "C" int vg_debug_attn_trace(void* buf) {
+  attn_tc_set_trace(buf);
+  return 0;
+}
 
 extern "C" int vg_set_attn_backend(int backend) {
   VG_REQUIRE(backend >= 0 && backend <= 2, -3, "vg_set_attn_backend: backend must be 0 (auto), 1 (simt) or 2 (tcgen05)");

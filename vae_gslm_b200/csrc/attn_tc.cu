@@ -16,6 +16,7 @@
 //   major bit differs).  dK/dV accumulate in TMEM across the loop; dQ_i is reduced into an fp32 buffer with
 //   vector red.global.add (as FlashAttention-2 does) and converted to bf16 by a tail kernel.
 #include <math_constants.h>
+#include <type_traits>
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -35,7 +36,13 @@ constexpr float kLn2 = 0.6931471805599453f;
 struct AttnTcShape {
   int B, H, Tq, Tk, q_offset;
   float scale;
+  unsigned long long* trace;      // debug: clock64 phase stamps of CTA (0,0,0), 8 per loop iteration (vg_debug_attn_trace)
 };
+// slot k of iteration `it`; one elected thread per role stamps
+#define AT_STAMP(it, k)                                                                                  \
+  do {                                                                                                   \
+    if (sh.trace && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (it) < 30) sh.trace[(it) * 8 + (k)] = clock64(); \
+  } while (0)
 
 // byte offset of the 16-byte piece `piece` (0..15: 8 bf16 each) of row `row` inside a [128 x 128] bf16 tile stored
 // as two [128 x 64] SWIZZLE_128B halves (what TMA would produce and what the UMMA descriptors expect)
@@ -120,28 +127,57 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive_expect_tx(v_full, TILE_BYTES);
       tma_load_3d(sV, &tmV, v_full, h * HD, j * TK, b);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The whole warp walks the loop and one ELECTED lane issues: inside a `lane == 0` branch the compiler wraps every
+    // tcgen05.mma in a per-thread ELECT / R2UR loop (~80 cycles per instruction against 32 cycles of tensor time for a
+    // 128x64x16 MMA); in warp-uniform code the descriptors stay in uniform registers and the MMAs issue back to back.
+    // S_{j+1} is issued BEFORE P_j·V: the softmax threads start on the next key tile while the tensor core finishes
+    // this one (they fold O_j one tile late).
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);     // S = Q·Kᵀ : both K-major
     constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);      // O = P·V  : A K-major, B (V) MN-major
-    const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aV = smem_u32(sV);
-    if (n_kt > 0) { mbar_wait(q_full, 0); }
-    for (int j = 0; j < n_kt; ++j) {
-      const int s = j & 1;
-      mbar_wait(&k_full[s], (j >> 1) & 1);
+    const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aV = smem_u32(sV), aK0 = smem_u32(sK);
+    if (n_kt > 0) {
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      const uint32_t aK = smem_u32(sK + s * TILE_BYTES);
+      AT_STAMP(0, 5);
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tS, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_s, k != 0);
-      umma_commit(&k_empty[s]);
-      umma_commit(s_full);
-      mbar_wait(p_full, j & 1);                 // P_j written (and S_j fully consumed)
+        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tS, desc_kmajor(aQ, k), desc_kmajor(aK0, k), idesc_s, k != 0);
+        umma_commit(&k_empty[0]);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    }
+    for (int j = 0; j < n_kt; ++j) {
+      AT_STAMP(j, 6);
+      mbar_wait(p_full, j & 1);                 // P_j written, S_j fully consumed, O_{j-1} folded
+      tc_fence_after();
+      AT_STAMP(j, 7);
+      if (j + 1 < n_kt) {
+        const int s = (j + 1) & 1;
+        mbar_wait(&k_full[s], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aK = aK0 + s * TILE_BYTES;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tS, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_s, k != 0);
+          umma_commit(&k_empty[s]);
+          umma_commit(s_full);
+        }
+        __syncwarp();
+        AT_STAMP(j + 1, 5);
+      }
       mbar_wait(v_full, j & 1);
       tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < TK / 16; ++k) umma_f16_ss(tO, desc_kmajor(aP, k), desc_mnmajor(aV, k), idesc_o, k != 0);
-      umma_commit(v_empty);
-      umma_commit(o_full);
+        for (int k = 0; k < TK / 16; ++k) umma_f16_ss(tO, desc_kmajor(aP, k), desc_mnmajor(aV, k), idesc_o, k != 0);
+        umma_commit(v_empty);
+        umma_commit(o_full);
+      }
+      __syncwarp();
     }
   } else if (warp >= 2) {
     // ===================== softmax (thread = query row) =====================
@@ -152,102 +188,84 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float slope2 = (slopes ? slopes[h] : 0.f) * kLog2e;
     const float scale2 = sh.scale * kLog2e;
     const uint32_t lane_addr = (uint32_t)rb << 16;
-    float m = -CUDART_INF_F, l = 0.f;
+    const int lim = min(ia + 1, klen);          // keys [0, lim) are visible to this row
+    const float rowc = -slope2 * (float)ia;
+    const f32x2_t sc2 = splat2(scale2), sl2 = splat2(slope2);
+    float m = -CUDART_INF_F, l = 0.f, corr_prev = 1.f;
     float o[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) o[d] = 0.f;
-
-    for (int j = 0; j < n_kt; ++j) {
+    // o = o·corr + O_j  (O_j = P_j·V_j from TMEM)
+    auto fold = [&](float corr) {
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tO + lane_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) o[c * 32 + e] = o[c * 32 + e] * corr + __uint_as_float(v[e]);
+      }
+    };
+    // One key tile.  The scores are formed two at a time with packed f32x2 FMAs: the ALiBi bias is an affine function of
+    // the column, s2 = S·scale2 + slope2·(j − i) (log2 domain).  MASKED tiles (the diagonal tile, or one that crosses
+    // kv_len) additionally replace columns ≥ lim by −inf; converting column indices to float per element, as the first
+    // version did, ran on the same XU pipe as the exponentials and tripled the cost of those tiles.
+    auto tile = [&](auto masked_tag, const int j) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       const int j0 = j * TK;
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // Tiles entirely below the diagonal and inside kv_len need no mask: the bias is an affine function of the
-      // column, so scores are formed two at a time with packed f32x2 FMAs (the softmax warps are issue-bound: the
-      // tensor pipe needs ~512 cycles per key tile, the scalar loops below ~3000).
-      const bool full_tile = (j0 + TK - 1 <= sh.q_offset + q0) && (j0 + TK <= klen);      // CTA-uniform
       float mx = -CUDART_INF_F;
-      float rsum = 0.f;
-      float m_new, m_use, corr;
-      if (full_tile) {
-        const float rowc = -slope2 * (float)ia;
-        const f32x2_t sc2 = splat2(scale2), sl2 = splat2(slope2);
-#pragma unroll 1
-        for (int c = 0; c < TK / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + lane_addr + c * 32, v);
-          tmem_ld_wait();
-          const f32x2_t cb0 = splat2(fmaf(slope2, (float)(j0 + c * 32), rowc));
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const f32x2_t cb = fma2(sl2, pack2((float)e, (float)(e + 1)), cb0);
-            float a, b;
-            unpack2(fma2(pack2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sc2, cb), a, b);
-            mx = fmaxf(mx, fmaxf(a, b));
-          }
-        }
-        m_new = fmaxf(m, mx);
-        m_use = m_new;                                       // finite: every key of the tile is visible
-        corr = ex2_approx(m - m_use);
-        f32x2_t rs2 = splat2(0.f);
-#pragma unroll 1
-        for (int c = 0; c < TK / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + lane_addr + c * 32, v);
-          tmem_ld_wait();
-          const f32x2_t cb0 = splat2(fmaf(slope2, (float)(j0 + c * 32), rowc) - m_use);
-          float p[32];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const f32x2_t cb = fma2(sl2, pack2((float)e, (float)(e + 1)), cb0);
-            float a, b;
-            unpack2(fma2(pack2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sc2, cb), a, b);
-            p[e] = ex2_approx(a);
-            p[e + 1] = ex2_approx(b);
-            rs2 = add2(rs2, pack2(p[e], p[e + 1]));
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 pk;
-            pk.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
-            pk.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-            pk.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
-            pk.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(sP + sw128_piece(r, c * 4 + g)) = pk;
-          }
-        }
-        float ra, rb;
-        unpack2(rs2, ra, rb);
-        rsum = ra + rb;
-      } else {
-      // pass 1: row maximum of the biased, masked scores (log2 domain)
 #pragma unroll 1
       for (int c = 0; c < TK / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tS + lane_addr + c * 32, v);
         tmem_ld_wait();
+        const f32x2_t cb0 = splat2(fmaf(slope2, (float)(j0 + c * 32), rowc));
+        const int nvalid = lim - (j0 + c * 32);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int ja = j0 + c * 32 + e;
-          const float s2 = __uint_as_float(v[e]) * scale2 - slope2 * (float)(ia - ja);
-          mx = fmaxf(mx, (ja <= ia && ja < klen) ? s2 : -CUDART_INF_F);
+        for (int e = 0; e < 32; e += 2) {
+          const f32x2_t cb = fma2(sl2, pack2((float)e, (float)(e + 1)), cb0);
+          float a, b;
+          unpack2(fma2(pack2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sc2, cb), a, b);
+          if (MASKED) {
+            a = (e < nvalid) ? a : -CUDART_INF_F;
+            b = (e + 1 < nvalid) ? b : -CUDART_INF_F;
+          }
+          mx = fmaxf(mx, fmaxf(a, b));
         }
       }
-      m_new = fmaxf(m, mx);
-      m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-      corr = ex2_approx(m - m_use);            // m = -inf → 0
-      // pass 2: P = exp2(s − m), written bf16 + swizzled as the A operand of the P·V MMA
+      if (threadIdx.x == 64) AT_STAMP(j, 1);
+      const float m_new = fmaxf(m, mx);
+      const float m_use = (MASKED && m_new == -CUDART_INF_F) ? 0.f : m_new;      // unmasked: every key is visible
+      const float corr = ex2_approx(m - m_use);                                   // m = -inf → 0
+      if (j > 0) {                              // O_{j-1} has long landed: fold it before P_j may be overwritten
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        if (threadIdx.x == 64) AT_STAMP(j, 3);
+        fold(corr_prev);
+        tc_fence_before();
+      }
+      if (threadIdx.x == 64) AT_STAMP(j, 4);
+      f32x2_t rs2 = splat2(0.f);
 #pragma unroll 1
       for (int c = 0; c < TK / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tS + lane_addr + c * 32, v);
         tmem_ld_wait();
+        const f32x2_t cb0 = splat2(fmaf(slope2, (float)(j0 + c * 32), rowc) - m_use);
+        const int nvalid = lim - (j0 + c * 32);
         float p[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int ja = j0 + c * 32 + e;
-          const float s2 = __uint_as_float(v[e]) * scale2 - slope2 * (float)(ia - ja);
-          p[e] = (ja <= ia && ja < klen) ? ex2_approx(s2 - m_use) : 0.f;
-          rsum += p[e];
+        for (int e = 0; e < 32; e += 2) {
+          const f32x2_t cb = fma2(sl2, pack2((float)e, (float)(e + 1)), cb0);
+          float a, b;
+          unpack2(fma2(pack2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sc2, cb), a, b);
+          if (MASKED) {
+            a = (e < nvalid) ? a : -CUDART_INF_F;
+            b = (e + 1 < nvalid) ? b : -CUDART_INF_F;
+          }
+          p[e] = ex2_approx(a);
+          p[e + 1] = ex2_approx(b);
+          rs2 = add2(rs2, pack2(p[e], p[e + 1]));
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -259,23 +277,29 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           *reinterpret_cast<uint4*>(sP + sw128_piece(r, c * 4 + g)) = pk;
         }
       }
-      }
-      l = l * corr + rsum;
+      float ra, rb2;
+      unpack2(rs2, ra, rb2);
+      l = l * corr + (ra + rb2);
       m = m_new;
-      tc_fence_before();            // our tcgen05.ld of S_j are ordered before the MMA that overwrites S
+      corr_prev = corr;
+    };
+
+    for (int j = 0; j < n_kt; ++j) {
+      const int j0 = j * TK;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (threadIdx.x == 64) AT_STAMP(j, 0);
+      const bool full_tile = (j0 + TK - 1 <= sh.q_offset + q0) && (j0 + TK <= klen);      // CTA-uniform
+      if (full_tile) tile(std::false_type{}, j); else tile(std::true_type{}, j);
+      tc_fence_before();            // our tcgen05.ld of S_j / O_{j-1} are ordered before the MMAs that overwrite them
       fence_proxy_async();          // generic-proxy writes of P visible to the tensor core (async proxy)
       mbar_arrive(p_full);
-      // fold O_j into the register accumulator
-      mbar_wait(o_full, j & 1);
+      if (threadIdx.x == 64) AT_STAMP(j, 2);
+    }
+    if (n_kt > 0) {
+      mbar_wait(o_full, (n_kt - 1) & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tO + lane_addr + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[c * 32 + e] = o[c * 32 + e] * corr + __uint_as_float(v[e]);
-      }
+      fold(corr_prev);
       tc_fence_before();
     }
     if (iq < sh.Tq) {
@@ -367,8 +391,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_3d(sQ + s * TILE_BYTES, &tmQ, &qdo_full[s], h * HD, q0, b);
       tma_load_3d(sdO + s * TILE_BYTES, &tmdO, &qdo_full[s], h * HD, q0, b);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues: see the forward) ==========
     constexpr uint32_t idesc_sp = make_idesc_bf16(128, 128, 0, 0);    // S = Q·Kᵀ, dP = dO·Vᵀ
     constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);      // dV = Pᵀ·dO, dK = dSᵀ·Q (A, B MN-major)
     constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);      // dQ = dS·K       (A K-major, B MN-major)
@@ -379,25 +403,40 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t aQ = smem_u32(sQ + s * TILE_BYTES), adO = smem_u32(sdO + s * TILE_BYTES);
       mbar_wait(&qdo_full[s], (it >> 1) & 1);      // (S/dP of the previous tile were consumed before pds_full(it-1))
       tc_fence_after();
+      AT_STAMP(it, 4);
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tS, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_sp, k != 0);
+        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tS, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_sp, k != 0);
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tdP, desc_kmajor(adO, k), desc_kmajor(aV, k), idesc_sp, k != 0);
-      umma_commit(sdp_full);
+        for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tdP, desc_kmajor(adO, k), desc_kmajor(aV, k), idesc_sp, k != 0);
+        umma_commit(sdp_full);
+      }
+      __syncwarp();
+      AT_STAMP(it, 5);
       mbar_wait(pds_full, it & 1);                 // P and dS in shared memory; dQ_{it-1} has been drained from TMEM
       tc_fence_after();
+      AT_STAMP(it, 6);
+      if (elect_one()) {
+        // dQ first: its drain (transpose + vector atomics, ~1.3 k cycles) is the longest consumer and runs while the
+        // tensor core works on dV, dK and the next tile's S / dP
 #pragma unroll
-      for (int k = 0; k < TQ / 16; ++k)
-        umma_f16_ss(tdV, desc_mnmajor(aP, k), desc_mnmajor(adO, k), idesc_t, (it | k) != 0);
+        for (int k = 0; k < TK / 16; ++k) umma_f16_ss(tdQ, desc_kmajor(adS, k), desc_mnmajor(aK, k), idesc_q, k != 0);
+        umma_commit(dq_full);
 #pragma unroll
-      for (int k = 0; k < TQ / 16; ++k)
-        umma_f16_ss(tdK, desc_mnmajor(adS, k), desc_mnmajor(aQ, k), idesc_t, (it | k) != 0);
+        for (int k = 0; k < TQ / 16; ++k)
+          umma_f16_ss(tdV, desc_mnmajor(aP, k), desc_mnmajor(adO, k), idesc_t, (it | k) != 0);
 #pragma unroll
-      for (int k = 0; k < TK / 16; ++k) umma_f16_ss(tdQ, desc_kmajor(adS, k), desc_mnmajor(aK, k), idesc_q, k != 0);
-      umma_commit(&qdo_empty[s]);
-      umma_commit(dq_full);
+        for (int k = 0; k < TQ / 16; ++k)
+          umma_f16_ss(tdK, desc_mnmajor(adS, k), desc_mnmajor(aQ, k), idesc_t, (it | k) != 0);
+        umma_commit(&qdo_empty[s]);
+      }
+      __syncwarp();
+      AT_STAMP(it, 7);
     }
-    if (n_it > 0) umma_commit(acc_full);
+    if (n_it > 0) {
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
+    }
   } else if (warp >= 2) {
     // ===================== softmax-backward threads (thread = query row of the current tile) =====================
     // warps 2..9: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.  With one warp per
@@ -431,21 +470,28 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) AT_STAMP(it, 0);
       // (key tile, query tile) pairs entirely below the diagonal with every row / key valid need no mask: packed
       // f32x2 arithmetic, two elements per FFMA2 / FMUL2 (the elementwise threads are issue-bound, see the forward)
       const bool full_pair = (j0 + TK - 1 <= sh.q_offset + q0) && (j0 + TK <= klen) && (q0 + TQ <= sh.Tq) &&
                              (sh.q_offset + q0 + TQ <= klen);                         // CTA-uniform
       const f32x2_t sc2 = splat2(scale2), sl2 = splat2(slope2), scl = splat2(sh.scale), ndl = splat2(-dl * sh.scale);
       const float rowc = -slope2 * (float)ia - L2;
+      const int lim = row_ok ? min(ia + 1, klen) : 0;             // keys [0, lim) are visible to this row
+      // P = exp2(S·scale2 + slope2·(j − i) − LSE2), dS = P·(dP − δ)·scale, two elements per packed FFMA2 / FMUL2 (the
+      // elementwise threads are issue- and XU-bound).  MASKED pairs zero P for columns ≥ lim with a select; the first
+      // version converted column indices to float per element on the XU pipe.
+      auto pair_tile = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll 1
-      for (int c = half * (TK / 32); c < (half + 1) * (TK / 32); ++c) {
-        uint32_t vs[16], vp[16];
-        tmem_ld_32x32b_x16(tS + lane_addr + c * 16, vs);
-        tmem_ld_32x32b_x16(tdP + lane_addr + c * 16, vp);
-        tmem_ld_wait();
-        float p[16], ds[16];
-        if (full_pair) {
+        for (int c = half * (TK / 32); c < (half + 1) * (TK / 32); ++c) {
+          uint32_t vs[16], vp[16];
+          tmem_ld_32x32b_x16(tS + lane_addr + c * 16, vs);
+          tmem_ld_32x32b_x16(tdP + lane_addr + c * 16, vp);
+          tmem_ld_wait();
+          float p[16], ds[16];
           const f32x2_t cb0 = splat2(fmaf(slope2, (float)(j0 + c * 16), rowc));
+          const int nvalid = lim - (j0 + c * 16);
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
             const f32x2_t cb = fma2(sl2, pack2((float)e, (float)(e + 1)), cb0);
@@ -453,37 +499,35 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             unpack2(fma2(pack2(__uint_as_float(vs[e]), __uint_as_float(vs[e + 1])), sc2, cb), a, bq);
             p[e] = ex2_approx(a);
             p[e + 1] = ex2_approx(bq);
+            if (MASKED) {
+              p[e] = (e < nvalid) ? p[e] : 0.f;
+              p[e + 1] = (e + 1 < nvalid) ? p[e + 1] : 0.f;
+            }
             const f32x2_t g2 = fma2(pack2(__uint_as_float(vp[e]), __uint_as_float(vp[e + 1])), scl, ndl);
             unpack2(mul2(pack2(p[e], p[e + 1]), g2), ds[e], ds[e + 1]);
           }
-        } else {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int ja = j0 + c * 16 + e;
-            const bool ok = row_ok && ja <= ia && ja < klen;
-            const float s2 = __uint_as_float(vs[e]) * scale2 - slope2 * (float)(ia - ja);
-            p[e] = ok ? ex2_approx(s2 - L2) : 0.f;
-            ds[e] = p[e] * (__uint_as_float(vp[e]) - dl) * sh.scale;
+          for (int g = 0; g < 2; ++g) {
+            uint4 pk, dk4;
+            pk.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);  pk.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+            pk.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);  pk.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+            dk4.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]); dk4.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
+            dk4.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]); dk4.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
+            const uint32_t off = sw128_piece(r, c * 2 + g);
+            *reinterpret_cast<uint4*>(sP + off) = pk;
+            *reinterpret_cast<uint4*>(sdS + off) = dk4;
           }
         }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint4 pk, dk4;
-          pk.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);  pk.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-          pk.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);  pk.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-          dk4.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]); dk4.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
-          dk4.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]); dk4.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
-          const uint32_t off = sw128_piece(r, c * 2 + g);
-          *reinterpret_cast<uint4*>(sP + off) = pk;
-          *reinterpret_cast<uint4*>(sdS + off) = dk4;
-        }
-      }
+      };
+      if (full_pair) pair_tile(std::false_type{}); else pair_tile(std::true_type{});
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(pds_full);
+      if (threadIdx.x == 64) AT_STAMP(it, 1);
       // dQ_i partial of this key tile → fp32 accumulator in global memory
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) AT_STAMP(it, 2);
       // thread-per-row vector atomics would touch 32 rows x 16 B per request (32 half-used sectors); each warp
       // transposes its 32 x 32 chunk through a private 4 KB XOR-swizzled scratch so that eight lanes cover one 128-byte
       // row segment: a request is four fully used lines
@@ -514,6 +558,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       tc_fence_before();
+      if (threadIdx.x == 64) AT_STAMP(it, 3);
     }
     // ---- dK / dV of this key tile (thread = key row)
     const int jr = j0 + r;
@@ -593,6 +638,8 @@ __global__ void attn_tc_dq_convert_kernel(const float* __restrict__ acc, __nv_bf
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+static unsigned long long* g_attn_trace = nullptr;
+void attn_tc_set_trace(void* buf) { g_attn_trace = (unsigned long long*)buf; }
 bool attn_tc_supported(int dtype, int64_t D, int64_t ld_q, int64_t ld_kv, const void* q, const void* k, const void* v,
                        int64_t kv_batch_stride, int64_t kv_head_stride) {
   return dtype == VG_BF16 && D == HD && ld_q % 8 == 0 && ld_kv % 8 == 0 && aligned(q, 16) && aligned(k, 16) &&
@@ -612,7 +659,7 @@ int attn_tc_fwd_launch(const void* q, const void* k, const void* v, int64_t ld_q
     VG_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     set = true;
   }
-  AttnTcShape sh{B, H, Tq, Tk, q_offset, scale};
+  AttnTcShape sh{B, H, Tq, Tk, q_offset, scale, g_attn_trace};
   dim3 grid((unsigned)((Tq + TQ - 1) / TQ), (unsigned)H, (unsigned)B);
   attn_tc_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, (__nv_bfloat16*)out, ld_out, lse, kv_len,
                                                           slopes, sh);
@@ -647,7 +694,7 @@ int attn_tc_bwd_launch(const void* dout, int64_t ld_dout, const void* q, const v
     VG_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     set = true;
   }
-  AttnTcShape sh{B, H, Tq, Tk, q_offset, scale};
+  AttnTcShape sh{B, H, Tq, Tk, q_offset, scale, g_attn_trace};
   dim3 grid((unsigned)((Tk + TK - 1) / TK), (unsigned)H, (unsigned)B);
   attn_tc_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, lse, delta, dq_acc,
                                                           (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, ld_dkv, kv_len,
