@@ -25,6 +25,8 @@ using namespace sm100;
 
 int make_tmap_bf16_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1,
                       int64_t stride2, int box0, int box1);
+int make_tmap_f32_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1,
+                     int64_t stride2, int box0, int box1);
 
 constexpr int TQ = 128;            // query rows per tile (UMMA M)
 constexpr int TK = 128;            // keys per tile
@@ -38,10 +40,16 @@ struct AttnTcShape {
   float scale;
   unsigned long long* trace;      // debug: clock64 phase stamps of CTA (0,0,0), 8 per loop iteration (vg_debug_attn_trace)
 };
-// slot k of iteration `it`; one elected thread per role stamps
-#define AT_STAMP(it, k)                                                                                  \
-  do {                                                                                                   \
-    if (sh.trace && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (it) < 30) sh.trace[(it) * 8 + (k)] = clock64(); \
+// slot k of iteration `it`; one elected thread per role stamps.  The traced CTA is the one whose linear block index is
+// stored in trace[255] by the host (tools/attn_trace.py); slots 240.. are whole-CTA marks.
+#define AT_ON() (sh.trace && (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) == (int)sh.trace[255])
+#define AT_STAMP(it, k)                                                    \
+  do {                                                                     \
+    if (AT_ON() && (it) < 30) sh.trace[(it) * 8 + (k)] = clock64();        \
+  } while (0)
+#define AT_MARK(k)                                       \
+  do {                                                   \
+    if (AT_ON()) sh.trace[240 + (k)] = clock64();        \
   } while (0)
 
 // byte offset of the 16-byte piece `piece` (0..15: 8 bf16 each) of row `row` inside a [128 x 128] bf16 tile stored
@@ -69,7 +77,7 @@ constexpr int FWD_SMEM = 5 * TILE_BYTES /*Q, K0, K1, V*/ + TILE_BYTES /*P second
 
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int64_t ld_out,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                    float* __restrict__ lse, const int32_t* __restrict__ kv_len, const float* __restrict__ slopes,
                    AttnTcShape sh) {
   extern __shared__ uint8_t smem_raw[];
@@ -85,10 +93,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 64) AT_MARK(0);
   // heavy (late) query tiles first: causal work grows with the tile index
   const int n_qt = (sh.Tq + TQ - 1) / TQ;
-  const int qt = n_qt - 1 - (int)blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  // 1-D grid, query tile slowest: every (head, batch) CTA of the heaviest tile is dispatched before any lighter one
+  const int qt = n_qt - 1 - (int)(blockIdx.x / (unsigned)(sh.H * sh.B));
+  const int hb = (int)(blockIdx.x % (unsigned)(sh.H * sh.B));
+  const int h = hb % sh.H, b = hb / sh.H;
   const int q0 = qt * TQ;
   const int klen = kv_len ? min(kv_len[b], sh.Tk) : sh.Tk;
   const int q_abs_last = sh.q_offset + min(q0 + TQ, sh.Tq) - 1;
@@ -96,13 +107,23 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int n_kt = (k_end + TK - 1) / TK;       // may be 0 (empty sequence)
 
   if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmO);
     mbar_init(q_full, 1);
     mbar_init(&k_full[0], 1); mbar_init(&k_full[1], 1);
     mbar_init(&k_empty[0], 1); mbar_init(&k_empty[1], 1);
     mbar_init(v_full, 1); mbar_init(v_empty, 1);
     mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
     fence_barrier_init();
+    // this thread is the TMA producer: the first tiles are requested before the CTA-wide set-up (TMEM allocation,
+    // barrier) so that their ~2 k cycles of latency overlap it
+    if (n_kt > 0) {
+      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, h * HD, q0, b);
+      mbar_arrive_expect_tx(&k_full[0], TILE_BYTES);
+      tma_load_3d(sK, &tmK, &k_full[0], h * HD, 0, b);
+      mbar_arrive_expect_tx(v_full, TILE_BYTES);
+      tma_load_3d(sV, &tmV, v_full, h * HD, 0, b);
+    }
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
   tc_fence_before();
@@ -111,14 +132,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base;            // columns [0,128): S
   const uint32_t tO = tmem_base + 128;      // columns [128,192): per-tile O_j
+  if (threadIdx.x == 64) AT_MARK(1);
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    if (n_kt > 0) {
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, h * HD, q0, b);
-    }
-    for (int j = 0; j < n_kt; ++j) {
+    for (int j = 1; j < n_kt; ++j) {
       const int s = j & 1;
       mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
       mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
@@ -302,10 +320,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fold(corr_prev);
       tc_fence_before();
     }
-    if (iq < sh.Tq) {
+    if (threadIdx.x == 64) AT_MARK(2);
+    // Output rows go through shared memory (the Q tile is dead after the last S MMA; each warp owns its 32 rows of it)
+    // in the SWIZZLE_128B box layout and leave as one TMA store per warp: thread-per-row 16-byte global stores touch
+    // 32 half-used sectors per request.  Rows beyond Tq are clipped by the tensor map.
+    {
       const bool valid = ia < klen && l > 0.f;
       const float inv = valid ? 1.f / l : 0.f;
-      __nv_bfloat16* op = out + ((int64_t)b * sh.Tq + iq) * ld_out + h * HD;
 #pragma unroll
       for (int g = 0; g < HD / 8; ++g) {
         uint4 pk;
@@ -313,14 +334,23 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         pk.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
         pk.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv);
         pk.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(op + g * 8) = pk;
+        *reinterpret_cast<uint4*>(sQ + r * 128 + ((g ^ (r & 7)) << 4)) = pk;
       }
-      lse[((int64_t)b * sh.H + h) * sh.Tq + iq] = valid ? (m + log2f(l)) * kLn2 : 0.f;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && q0 + rb < sh.Tq) {
+        tma_store_3d(&tmO, sQ + rb * 128, h * HD, q0 + rb, b);
+        tma_store_commit();
+      }
+      if (iq < sh.Tq) lse[((int64_t)b * sh.H + h) * sh.Tq + iq] = valid ? (m + log2f(l)) * kLn2 : 0.f;
+      if (lane == 0) tma_store_wait_read<0>();
     }
   }
+  if (threadIdx.x == 64) AT_MARK(3);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (threadIdx.x == 64) AT_MARK(4);
 }
 
 // =========================================================================================== backward
@@ -331,8 +361,9 @@ constexpr int BWD_SMEM = 10 * TILE_BYTES + 8 * 4096 /* dQ transpose scratch */ +
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                   const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
-                   __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int64_t ld_dkv,
+                   const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
+                   const __grid_constant__ CUtensorMap tmDV, const float* __restrict__ lse,
+                   const float* __restrict__ delta,
                    const int32_t* __restrict__ kv_len, const float* __restrict__ slopes, AttnTcShape sh) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -346,11 +377,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sDQ = smem + 10 * TILE_BYTES;      // 8 warps x 4 KB dQ transpose scratch
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE_BYTES + 8 * 4096);
   uint64_t *kv_full = bars, *qdo_full = bars + 1, *qdo_empty = bars + 3, *sdp_full = bars + 5, *pds_full = bars + 6,
-           *dq_full = bars + 7, *acc_full = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+           *dq_full = bars + 7, *acc_full = bars + 8, *mma_done = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (threadIdx.x == 64) AT_MARK(0);
+  // 1-D grid, key tile slowest: key tile 0 loops over every query tile, so all its (head, batch) CTAs go first
+  const int kt = (int)(blockIdx.x / (unsigned)(sh.H * sh.B));
+  const int hb = (int)(blockIdx.x % (unsigned)(sh.H * sh.B));
+  const int h = hb % sh.H, b = hb / sh.H;
   const int j0 = kt * TK;
   const int klen = kv_len ? min(kv_len[b], sh.Tk) : sh.Tk;
   // query tiles that can see key j0: q_offset + iq >= j0; rows at/after klen are padded queries (P = 0)
@@ -362,11 +397,21 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
-    mbar_init(kv_full, 1);
+    prefetch_tensormap(&tmDQ); prefetch_tensormap(&tmDK); prefetch_tensormap(&tmDV);
+    mbar_init(kv_full, 1); mbar_init(mma_done, 1);
     mbar_init(&qdo_full[0], 1); mbar_init(&qdo_full[1], 1);
     mbar_init(&qdo_empty[0], 1); mbar_init(&qdo_empty[1], 1);
     mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(dq_full, 1); mbar_init(acc_full, 1);
     fence_barrier_init();
+    // this thread is the TMA producer: first tiles requested before the CTA-wide set-up (see the forward)
+    if (n_it > 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
+      tma_load_3d(sK, &tmK, kv_full, h * HD, j0, b);
+      tma_load_3d(sV, &tmV, kv_full, h * HD, j0, b);
+      mbar_arrive_expect_tx(&qdo_full[0], 2 * TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, &qdo_full[0], h * HD, i_first * TQ, b);
+      tma_load_3d(sdO, &tmdO, &qdo_full[0], h * HD, i_first * TQ, b);
+    }
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
@@ -375,15 +420,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
                  tdQ = tmem_base + 384;
+  if (threadIdx.x == 64) AT_MARK(1);
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    if (n_it > 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
-      tma_load_3d(sK, &tmK, kv_full, h * HD, j0, b);
-      tma_load_3d(sV, &tmV, kv_full, h * HD, j0, b);
-    }
-    for (int it = 0; it < n_it; ++it) {
+    for (int it = 1; it < n_it; ++it) {
       const int s = it & 1;
       const int q0 = (i_first + it) * TQ;
       mbar_wait(&qdo_empty[s], ((it >> 1) & 1) ^ 1);
@@ -397,13 +438,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);      // dV = Pᵀ·dO, dK = dSᵀ·Q (A, B MN-major)
     constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);      // dQ = dS·K       (A K-major, B MN-major)
     const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
-    if (n_it > 0) mbar_wait(kv_full, 0);
-    for (int it = 0; it < n_it; ++it) {
+    // tensor-core order per query tile:  dQ_it (its drain is the next thing the elementwise warps do)  →  S, dP of
+    // tile it+1 (so that they are ready when the drain ends)  →  dV, dK of tile it.  The N = 64 MMAs read 6 KB of
+    // shared memory per 32 tensor cycles and are shared-memory-bandwidth bound (~48 cycles each).
+    auto issue_sdp = [&](int it) {
       const int s = it & 1;
       const uint32_t aQ = smem_u32(sQ + s * TILE_BYTES), adO = smem_u32(sdO + s * TILE_BYTES);
-      mbar_wait(&qdo_full[s], (it >> 1) & 1);      // (S/dP of the previous tile were consumed before pds_full(it-1))
+      mbar_wait(&qdo_full[s], (it >> 1) & 1);
       tc_fence_after();
-      AT_STAMP(it, 4);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_f16_ss(tS, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_sp, k != 0);
@@ -412,16 +454,30 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(sdp_full);
       }
       __syncwarp();
-      AT_STAMP(it, 5);
-      mbar_wait(pds_full, it & 1);                 // P and dS in shared memory; dQ_{it-1} has been drained from TMEM
+    };
+    if (n_it > 0) {
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      AT_STAMP(0, 5);
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1;
+      const uint32_t aQ = smem_u32(sQ + s * TILE_BYTES), adO = smem_u32(sdO + s * TILE_BYTES);
+      mbar_wait(pds_full, it & 1);                 // P and dS in shared memory; S, dP consumed; dQ_{it-1} drained
       tc_fence_after();
       AT_STAMP(it, 6);
       if (elect_one()) {
-        // dQ first: its drain (transpose + vector atomics, ~1.3 k cycles) is the longest consumer and runs while the
-        // tensor core works on dV, dK and the next tile's S / dP
 #pragma unroll
         for (int k = 0; k < TK / 16; ++k) umma_f16_ss(tdQ, desc_kmajor(adS, k), desc_mnmajor(aK, k), idesc_q, k != 0);
         umma_commit(dq_full);
+      }
+      __syncwarp();
+      AT_STAMP(it, 4);
+      if (it + 1 < n_it) {
+        issue_sdp(it + 1);
+        AT_STAMP(it + 1, 5);
+      }
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < TQ / 16; ++k)
           umma_f16_ss(tdV, desc_mnmajor(aP, k), desc_mnmajor(adO, k), idesc_t, (it | k) != 0);
@@ -429,6 +485,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int k = 0; k < TQ / 16; ++k)
           umma_f16_ss(tdK, desc_mnmajor(adS, k), desc_mnmajor(aQ, k), idesc_t, (it | k) != 0);
         umma_commit(&qdo_empty[s]);
+        umma_commit(mma_done);                     // P / dS of this tile may be overwritten
       }
       __syncwarp();
       AT_STAMP(it, 7);
@@ -506,6 +563,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const f32x2_t g2 = fma2(pack2(__uint_as_float(vp[e]), __uint_as_float(vp[e + 1])), scl, ndl);
             unpack2(mul2(pack2(p[e], p[e + 1]), g2), ds[e], ds[e + 1]);
           }
+          // the previous tile's dQ / dV / dK MMAs still read P and dS from shared memory while this tile's first chunk is
+          // computed: wait for them only here, before the first store
+          if (c == half * (TK / 32) && it > 0) mbar_wait(mma_done, (it - 1) & 1);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             uint4 pk, dk4;
@@ -528,50 +588,47 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
       if (threadIdx.x == 64) AT_STAMP(it, 2);
-      // thread-per-row vector atomics would touch 32 rows x 16 B per request (32 half-used sectors); each warp
-      // transposes its 32 x 32 chunk through a private 4 KB XOR-swizzled scratch so that eight lanes cover one 128-byte
-      // row segment: a request is four fully used lines
+      // Each warp writes its 32 rows x 32 columns (thread = row, 128-byte rows, 16-byte pieces XOR-swizzled: exactly
+      // the SWIZZLE_128B box layout) into a private 4 KB scratch and ONE lane hands the box to the TMA unit as a bulk
+      // reduce-add (cp.reduce.async.bulk.tensor): rows beyond Tq are clipped by the tensor map.  The first version
+      // read the scratch back and issued eight 16-byte vector atomics per thread — 1.3-1.7 k cycles per tile on the
+      // critical path of the loop.
       {
         uint8_t* scr = sDQ + (warp - 2) * 4096;
-        const int rows_valid = min(32, max(0, q_valid_end - (q0 + rb)));
-        const int64_t dq_pitch = (int64_t)sh.H * HD;
-        float* dq_base = dq_acc + ((int64_t)b * sh.Tq + q0 + rb) * dq_pitch + h * HD;
-        {
-          const int c = half;                      // this warp's 32 of the 64 head-dim columns
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tdQ + lane_addr + c * 32, v);
-          tmem_ld_wait();
+        if (lane == 0) tma_store_wait_read<0>();        // the previous tile's reduce has finished reading the scratch
+        __syncwarp();
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tdQ + lane_addr + half * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(scr + lane * 128 + ((g ^ (lane & 7)) << 4)) =
-                make_uint4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int itr = 0; itr < 8; ++itr) {
-            const int row = itr * 4 + (lane >> 3), slot = lane & 7;
-            if (row < rows_valid) {
-              const float4 f = *reinterpret_cast<const float4*>(scr + row * 128 + ((slot ^ (row & 7)) << 4));
-              atomicAdd(reinterpret_cast<float4*>(dq_base + row * dq_pitch + c * 32 + slot * 4), f);
-            }
-          }
-          __syncwarp();
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(scr + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+              make_uint4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_3d(&tmDQ, scr, h * HD + half * 32, q0 + rb, b);
+          tma_store_commit();
         }
       }
       tc_fence_before();
       if (threadIdx.x == 64) AT_STAMP(it, 3);
     }
-    // ---- dK / dV of this key tile (thread = key row)
-    const int jr = j0 + r;
+    if (threadIdx.x == 64) AT_MARK(2);
+    // ---- dK / dV of this key tile (thread = key row): the `half` 0 warps store dV, the `half` 1 warps dK — each its
+    // TMEM quadrant's 32 rows x 64 columns, bf16, through its 4 KB scratch (SWIZZLE_128B box) and one TMA store; rows
+    // beyond Tk are clipped by the tensor map
     if (n_it > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
     }
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-      __nv_bfloat16* dst = (which == 0 ? dv : dk) + ((int64_t)b * sh.Tk + jr) * ld_dkv + h * HD;
-      const uint32_t tsrc = (which == 0 ? tdV : tdK) + lane_addr;
-      {
-        const int c = half;
+    {
+      uint8_t* scr = sDQ + (warp - 2) * 4096;
+      if (lane == 0) tma_store_wait_read<0>();        // the last dQ reduce has finished reading the scratch
+      __syncwarp();
+      const uint32_t tsrc = (half == 0 ? tdV : tdK) + lane_addr;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         if (n_it > 0) {
           tmem_ld_32x32b_x32(tsrc + c * 32, v);
@@ -580,23 +637,31 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = 0u;
         }
-        if (jr < sh.Tk) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
-            pk.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
-            pk.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
-            pk.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
-          }
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(scr + lane * 128 + (((c * 4 + g) ^ (lane & 7)) << 4)) = pk;
         }
       }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && j0 + rb < sh.Tk) {
+        tma_store_3d(half == 0 ? &tmDV : &tmDK, scr, h * HD, j0 + rb, b);
+        tma_store_commit();
+      }
+      if (lane == 0) tma_store_wait_all();             // this lane's dQ reductions and its dK / dV store are complete
     }
+    if (threadIdx.x == 64) AT_MARK(5);
   }
+  if (threadIdx.x == 64) AT_MARK(3);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 64) AT_MARK(4);
 }
 
 // delta[b,h,i] = Σ_d dO[i,d]·O[i,d]   (bf16 inputs)
@@ -654,15 +719,16 @@ int attn_tc_fwd_launch(const void* q, const void* k, const void* v, int64_t ld_q
   if ((rc = make_tmap_bf16_3d(&tmQ, q, (int64_t)H * HD, Tq, B, ld_q, (int64_t)Tq * ld_q, HD, TQ))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmK, k, (int64_t)H * HD, Tk, B, ld_kv, (int64_t)Tk * ld_kv, HD, TK))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmV, v, (int64_t)H * HD, Tk, B, ld_kv, (int64_t)Tk * ld_kv, HD, TK))) return rc;
+  CUtensorMap tmO;           // output rows leave as one [32 x 64] box per warp
+  if ((rc = make_tmap_bf16_3d(&tmO, out, (int64_t)H * HD, Tq, B, ld_out, (int64_t)Tq * ld_out, HD, 32))) return rc;
   static bool set = false;
   if (!set) {
     VG_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     set = true;
   }
   AttnTcShape sh{B, H, Tq, Tk, q_offset, scale, g_attn_trace};
-  dim3 grid((unsigned)((Tq + TQ - 1) / TQ), (unsigned)H, (unsigned)B);
-  attn_tc_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, (__nv_bfloat16*)out, ld_out, lse, kv_len,
-                                                          slopes, sh);
+  dim3 grid((unsigned)((Tq + TQ - 1) / TQ) * (unsigned)H * (unsigned)B);
+  attn_tc_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, tmO, lse, kv_len, slopes, sh);
   VG_LAUNCH_CHECK("vg_attn_fwd(tcgen05)");
   return 0;
 }
@@ -689,15 +755,20 @@ int attn_tc_bwd_launch(const void* dout, int64_t ld_dout, const void* q, const v
   if ((rc = make_tmap_bf16_3d(&tmK, k, (int64_t)H * HD, Tk, B, ld_kv, (int64_t)Tk * ld_kv, HD, TK))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmV, v, (int64_t)H * HD, Tk, B, ld_kv, (int64_t)Tk * ld_kv, HD, TK))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmdO, dout, (int64_t)H * HD, Tq, B, ld_dout, (int64_t)Tq * ld_dout, HD, TQ))) return rc;
+  CUtensorMap tmDQ;          // fp32 dQ accumulator [B, Tq, H*64]: reduce-add boxes of 32 rows x 32 columns
+  if ((rc = make_tmap_f32_3d(&tmDQ, dq_acc, (int64_t)H * HD, Tq, B, (int64_t)H * HD, (int64_t)Tq * H * HD, 32, 32)))
+    return rc;
+  CUtensorMap tmDK, tmDV;    // dK / dV rows leave as [32 x 64] boxes
+  if ((rc = make_tmap_bf16_3d(&tmDK, dk, (int64_t)H * HD, Tk, B, ld_dkv, (int64_t)Tk * ld_dkv, HD, 32))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmDV, dv, (int64_t)H * HD, Tk, B, ld_dkv, (int64_t)Tk * ld_dkv, HD, 32))) return rc;
   static bool set = false;
   if (!set) {
     VG_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     set = true;
   }
   AttnTcShape sh{B, H, Tq, Tk, q_offset, scale, g_attn_trace};
-  dim3 grid((unsigned)((Tk + TK - 1) / TK), (unsigned)H, (unsigned)B);
-  attn_tc_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, lse, delta, dq_acc,
-                                                          (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, ld_dkv, kv_len,
+  dim3 grid((unsigned)((Tk + TK - 1) / TK) * (unsigned)H * (unsigned)B);
+  attn_tc_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, tmDK, tmDV, lse, delta, kv_len,
                                                           slopes, sh);
   VG_LAUNCH_CHECK("vg_attn_bwd(tcgen05)");
   const int C = H * HD;

@@ -72,6 +72,24 @@ int make_tmap_bf16_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1
   return 0;
 }
 
+// 3-D fp32 tensor map for bulk reduce-add of [box1 x 32] tiles (128-byte rows, SWIZZLE_128B): the fp32 dQ accumulator
+// of the attention backward.  Strides in elements.
+int make_tmap_f32_3d(CUtensorMap* map, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1,
+                     int64_t stride2, int box0, int box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  VG_REQUIRE(fn != nullptr, -20, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)stride1 * 4, (cuuint64_t)stride2 * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VG_REQUIRE(r == CUDA_SUCCESS, -21, "cuTensorMapEncodeTiled(3d f32) failed (CUresult %d) dims=%lld,%lld,%lld", (int)r,
+             (long long)d0, (long long)d1, (long long)d2);
+  return 0;
+}
+
 bool gemm_tc_supported(const vg_gemm_args* a) {
   if (a->ab_dtype != VG_BF16) return false;
   if (a->M < 1 || a->N < 8 || a->K < 8) return false;
