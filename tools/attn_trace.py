@@ -47,5 +47,5 @@ for blk in blocks:
     print(f"==== block {blk}")
     show("forward", fwd, ["softmax: S ready", "pass-1 done", "P published", "O_j ready", "O folded",
                           "mma: S(j) issued", "P(j-1)V issued", "P ready"])
-    show("backward", bwd, ["elementwise: S,dP ready", "P,dS published", "dQ ready", "dQ drained",
+    show("backward", bwd, ["elementwise: S,dP ready", "math done", "P,dS published", "dQ(it-1) drained",
                            "mma: dQ issued", "S,dP(it) issued", "P,dS ready", "dV,dK issued"])

@@ -377,8 +377,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sDQ = smem + 10 * TILE_BYTES;      // 8 warps x 4 KB dQ transpose scratch
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE_BYTES + 8 * 4096);
   uint64_t *kv_full = bars, *qdo_full = bars + 1, *qdo_empty = bars + 3, *sdp_full = bars + 5, *pds_full = bars + 6,
-           *dq_full = bars + 7, *acc_full = bars + 8, *mma_done = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+           *dq_full = bars + 7 /* 2: one per dQ buffer */, *acc_full = bars + 9, *mma_done = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 64) AT_MARK(0);
@@ -401,7 +401,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(kv_full, 1); mbar_init(mma_done, 1);
     mbar_init(&qdo_full[0], 1); mbar_init(&qdo_full[1], 1);
     mbar_init(&qdo_empty[0], 1); mbar_init(&qdo_empty[1], 1);
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(dq_full, 1); mbar_init(acc_full, 1);
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(&dq_full[0], 1); mbar_init(&dq_full[1], 1);
+    mbar_init(acc_full, 1);
     fence_barrier_init();
     // this thread is the TMA producer: first tiles requested before the CTA-wide set-up (see the forward)
     if (n_it > 0) {
@@ -419,7 +420,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
-                 tdQ = tmem_base + 384;
+                 tdQ = tmem_base + 384;      // two buffers of 64 columns: dQ of tile it lives in buffer it & 1
   if (threadIdx.x == 64) AT_MARK(1);
 
   if (warp == 0 && lane == 0) {
@@ -438,9 +439,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);      // dV = Pᵀ·dO, dK = dSᵀ·Q (A, B MN-major)
     constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);      // dQ = dS·K       (A K-major, B MN-major)
     const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
-    // tensor-core order per query tile:  dQ_it (its drain is the next thing the elementwise warps do)  →  S, dP of
-    // tile it+1 (so that they are ready when the drain ends)  →  dV, dK of tile it.  The N = 64 MMAs read 6 KB of
-    // shared memory per 32 tensor cycles and are shared-memory-bandwidth bound (~48 cycles each).
+    // tensor-core order once P, dS of tile `it` are published:  S, dP of tile it+1 (the elementwise warps start on them
+    // at once)  →  dQ_it  →  dV, dK of tile it.  The N = 64 MMAs read 6 KB of shared memory per 32 tensor cycles and are
+    // shared-memory-bandwidth bound (~48 cycles each).
     auto issue_sdp = [&](int it) {
       const int s = it & 1;
       const uint32_t aQ = smem_u32(sQ + s * TILE_BYTES), adO = smem_u32(sdO + s * TILE_BYTES);
@@ -466,17 +467,18 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(pds_full, it & 1);                 // P and dS in shared memory; S, dP consumed; dQ_{it-1} drained
       tc_fence_after();
       AT_STAMP(it, 6);
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < TK / 16; ++k) umma_f16_ss(tdQ, desc_kmajor(adS, k), desc_mnmajor(aK, k), idesc_q, k != 0);
-        umma_commit(dq_full);
-      }
-      __syncwarp();
-      AT_STAMP(it, 4);
       if (it + 1 < n_it) {
         issue_sdp(it + 1);
         AT_STAMP(it + 1, 5);
       }
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k)
+          umma_f16_ss(tdQ + s * 64, desc_kmajor(adS, k), desc_mnmajor(aK, k), idesc_q, k != 0);
+        umma_commit(&dq_full[s]);
+      }
+      __syncwarp();
+      AT_STAMP(it, 4);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < TQ / 16; ++k)
@@ -513,6 +515,33 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int iq0 = i_first * TQ + r;
       if (iq0 < sh.Tq && sh.q_offset + iq0 < klen) { lse_next = lse_row[iq0]; delta_next = delta_row[iq0]; }
     }
+    // dQ partial of query tile `t` (this key tile's contribution) → fp32 accumulator in global memory.  Each warp writes
+    // its 32 rows x 32 columns (thread = row, 128-byte rows, 16-byte pieces XOR-swizzled: exactly the SWIZZLE_128B box
+    // layout) into a private 4 KB scratch and ONE lane hands the box to the TMA unit as a bulk reduce-add
+    // (cp.reduce.async.bulk.tensor); rows beyond Tq are clipped by the tensor map.  The first version read the scratch
+    // back and issued eight 16-byte vector atomics per thread — 1.3-1.7 k cycles per tile on the loop's critical path.
+    // It runs one tile late (dQ is double-buffered in TMEM), in the bubble after P / dS of the next tile are published.
+    auto drain_dq = [&](int t) {
+      uint8_t* scr = sDQ + (warp - 2) * 4096;
+      mbar_wait(&dq_full[t & 1], (t >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) tma_store_wait_read<0>();        // the previous reduce has finished reading the scratch
+      __syncwarp();
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tdQ + (t & 1) * 64 + lane_addr + half * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<uint4*>(scr + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+            make_uint4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_3d(&tmDQ, scr, h * HD + half * 32, (i_first + t) * TQ + rb, b);
+        tma_store_commit();
+      }
+    };
     for (int it = 0; it < n_it; ++it) {
       const int q0 = (i_first + it) * TQ;
       const int iq = q0 + r;
@@ -538,82 +567,63 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // P = exp2(S·scale2 + slope2·(j − i) − LSE2), dS = P·(dP − δ)·scale, two elements per packed FFMA2 / FMUL2 (the
       // elementwise threads are issue- and XU-bound).  MASKED pairs zero P for columns ≥ lim with a select; the first
       // version converted column indices to float per element on the XU pipe.
+      // The results stay in registers (64 columns x {P, dS} as packed bf16 pairs) until the previous tile's dQ / dV /
+      // dK MMAs have finished reading P and dS from shared memory: only the short burst of stores waits for them, the
+      // exponentials of this tile overlap them.
+      uint32_t pkp[32], pkd[32];
       auto pair_tile = [&](auto masked_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
-#pragma unroll 1
-        for (int c = half * (TK / 32); c < (half + 1) * (TK / 32); ++c) {
+#pragma unroll
+        for (int cc = 0; cc < TK / 32; ++cc) {
+          const int c = half * (TK / 32) + cc;
           uint32_t vs[16], vp[16];
           tmem_ld_32x32b_x16(tS + lane_addr + c * 16, vs);
           tmem_ld_32x32b_x16(tdP + lane_addr + c * 16, vp);
           tmem_ld_wait();
-          float p[16], ds[16];
           const f32x2_t cb0 = splat2(fmaf(slope2, (float)(j0 + c * 16), rowc));
           const int nvalid = lim - (j0 + c * 16);
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
             const f32x2_t cb = fma2(sl2, pack2((float)e, (float)(e + 1)), cb0);
-            float a, bq;
+            float a, bq, p0, p1, d0, d1;
             unpack2(fma2(pack2(__uint_as_float(vs[e]), __uint_as_float(vs[e + 1])), sc2, cb), a, bq);
-            p[e] = ex2_approx(a);
-            p[e + 1] = ex2_approx(bq);
+            p0 = ex2_approx(a);
+            p1 = ex2_approx(bq);
             if (MASKED) {
-              p[e] = (e < nvalid) ? p[e] : 0.f;
-              p[e + 1] = (e + 1 < nvalid) ? p[e + 1] : 0.f;
+              p0 = (e < nvalid) ? p0 : 0.f;
+              p1 = (e + 1 < nvalid) ? p1 : 0.f;
             }
             const f32x2_t g2 = fma2(pack2(__uint_as_float(vp[e]), __uint_as_float(vp[e + 1])), scl, ndl);
-            unpack2(mul2(pack2(p[e], p[e + 1]), g2), ds[e], ds[e + 1]);
-          }
-          // the previous tile's dQ / dV / dK MMAs still read P and dS from shared memory while this tile's first chunk is
-          // computed: wait for them only here, before the first store
-          if (c == half * (TK / 32) && it > 0) mbar_wait(mma_done, (it - 1) & 1);
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 pk, dk4;
-            pk.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);  pk.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-            pk.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);  pk.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-            dk4.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]); dk4.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
-            dk4.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]); dk4.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
-            const uint32_t off = sw128_piece(r, c * 2 + g);
-            *reinterpret_cast<uint4*>(sP + off) = pk;
-            *reinterpret_cast<uint4*>(sdS + off) = dk4;
+            unpack2(mul2(pack2(p0, p1), g2), d0, d1);
+            pkp[cc * 8 + e / 2] = pack_bf16x2(p0, p1);
+            pkd[cc * 8 + e / 2] = pack_bf16x2(d0, d1);
           }
         }
       };
       if (full_pair) pair_tile(std::false_type{}); else pair_tile(std::true_type{});
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(pds_full);
+      tc_fence_before();                              // S / dP of this tile are consumed
       if (threadIdx.x == 64) AT_STAMP(it, 1);
-      // dQ_i partial of this key tile → fp32 accumulator in global memory
-      mbar_wait(dq_full, it & 1);
-      tc_fence_after();
-      if (threadIdx.x == 64) AT_STAMP(it, 2);
-      // Each warp writes its 32 rows x 32 columns (thread = row, 128-byte rows, 16-byte pieces XOR-swizzled: exactly
-      // the SWIZZLE_128B box layout) into a private 4 KB scratch and ONE lane hands the box to the TMA unit as a bulk
-      // reduce-add (cp.reduce.async.bulk.tensor): rows beyond Tq are clipped by the tensor map.  The first version
-      // read the scratch back and issued eight 16-byte vector atomics per thread — 1.3-1.7 k cycles per tile on the
-      // critical path of the loop.
-      {
-        uint8_t* scr = sDQ + (warp - 2) * 4096;
-        if (lane == 0) tma_store_wait_read<0>();        // the previous tile's reduce has finished reading the scratch
-        __syncwarp();
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tdQ + lane_addr + half * 32, v);
-        tmem_ld_wait();
+      if (it > 0) mbar_wait(mma_done, (it - 1) & 1);  // the previous tile's MMAs no longer read P / dS
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<uint4*>(scr + lane * 128 + ((g ^ (lane & 7)) << 4)) =
-              make_uint4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_reduce_add_3d(&tmDQ, scr, h * HD + half * 32, q0 + rb, b);
-          tma_store_commit();
+      for (int cc = 0; cc < TK / 32; ++cc) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t off = sw128_piece(r, (half * (TK / 32) + cc) * 2 + g);
+          *reinterpret_cast<uint4*>(sP + off) =
+              make_uint4(pkp[cc * 8 + g * 4 + 0], pkp[cc * 8 + g * 4 + 1], pkp[cc * 8 + g * 4 + 2], pkp[cc * 8 + g * 4 + 3]);
+          *reinterpret_cast<uint4*>(sdS + off) =
+              make_uint4(pkd[cc * 8 + g * 4 + 0], pkd[cc * 8 + g * 4 + 1], pkd[cc * 8 + g * 4 + 2], pkd[cc * 8 + g * 4 + 3]);
         }
       }
-      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(pds_full);
+      if (threadIdx.x == 64) AT_STAMP(it, 2);
+      // while the tensor core forms S, dP of the next tile: dQ of the PREVIOUS tile (the other TMEM buffer; dQ of this
+      // tile is only being issued now) goes to the global accumulator
+      if (it > 0) drain_dq(it - 1);
       if (threadIdx.x == 64) AT_STAMP(it, 3);
     }
+    if (n_it > 0) drain_dq(n_it - 1);
     if (threadIdx.x == 64) AT_MARK(2);
     // ---- dK / dV of this key tile (thread = key row): the `half` 0 warps store dV, the `half` 1 warps dK — each its
     // TMEM quadrant's 32 rows x 64 columns, bf16, through its 4 KB scratch (SWIZZLE_128B box) and one TMA store; rows
