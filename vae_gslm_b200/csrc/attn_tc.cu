@@ -354,9 +354,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // =========================================================================================== backward
-constexpr int BWD_THREADS = 320;            // 2 control warps + 8 elementwise warps (two per TMEM lane quadrant)
-// layout: K | V | Q0 | Q1 | dO0 | dO1 | P (2 halves) | dS (2 halves) = 10 tiles
-constexpr int BWD_SMEM = 10 * TILE_BYTES + 8 * 4096 /* dQ transpose scratch */ + 1024 + 256;
+constexpr int BWD_EW = 16;                  // elementwise warps: four per TMEM lane quadrant, 32 of the 128 key columns each
+constexpr int BWD_THREADS = 64 + 32 * BWD_EW;      // + TMA producer warp + MMA issuer warp
+// layout: K | V | Q x3 | dO x3 | P (2 halves) | dS (2 halves) = 12 tiles
+constexpr int BWD_QS = 3;                   // Q / dO ring stages: a stage is free only after dV, dK of its tile (the LAST MMAs
+                                            // of an iteration); with 2 stages the ~1.3 k cycle reload was exposed every tile
+constexpr int BWD_SMEM = (6 + 2 * BWD_QS) * TILE_BYTES + 8 * 4096 /* dQ / dK / dV scratch */ + 1024 + 256;
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -370,15 +373,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sK = smem;
   uint8_t* sV = smem + TILE_BYTES;
-  uint8_t* sQ = smem + 2 * TILE_BYTES;        // 2 stages
-  uint8_t* sdO = smem + 4 * TILE_BYTES;       // 2 stages
-  uint8_t* sP = smem + 6 * TILE_BYTES;        // 2 halves
-  uint8_t* sdS = smem + 8 * TILE_BYTES;       // 2 halves
-  uint8_t* sDQ = smem + 10 * TILE_BYTES;      // 8 warps x 4 KB dQ transpose scratch
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * TILE_BYTES + 8 * 4096);
-  uint64_t *kv_full = bars, *qdo_full = bars + 1, *qdo_empty = bars + 3, *sdp_full = bars + 5, *pds_full = bars + 6,
-           *dq_full = bars + 7 /* 2: one per dQ buffer */, *acc_full = bars + 9, *mma_done = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint8_t* sQ = smem + 2 * TILE_BYTES;                       // BWD_QS stages
+  uint8_t* sdO = smem + (2 + BWD_QS) * TILE_BYTES;           // BWD_QS stages
+  uint8_t* sP = smem + (2 + 2 * BWD_QS) * TILE_BYTES;        // 2 halves
+  uint8_t* sdS = smem + (4 + 2 * BWD_QS) * TILE_BYTES;       // 2 halves
+  uint8_t* sDQ = smem + (6 + 2 * BWD_QS) * TILE_BYTES;       // 8 warps x 4 KB dQ transpose scratch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + 8 * 4096);
+  uint64_t *kv_full = bars, *qdo_full = bars + 1 /* 3 */, *qdo_empty = bars + 4 /* 3 */, *sdp_full = bars + 7,
+           *pds_full = bars + 8, *dq_full = bars + 9 /* 2: one per dQ buffer */, *acc_full = bars + 11,
+           *mma_done = bars + 12, *sdp_free = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 64) AT_MARK(0);
@@ -399,9 +403,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
     prefetch_tensormap(&tmDQ); prefetch_tensormap(&tmDK); prefetch_tensormap(&tmDV);
     mbar_init(kv_full, 1); mbar_init(mma_done, 1);
-    mbar_init(&qdo_full[0], 1); mbar_init(&qdo_full[1], 1);
-    mbar_init(&qdo_empty[0], 1); mbar_init(&qdo_empty[1], 1);
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 256); mbar_init(&dq_full[0], 1); mbar_init(&dq_full[1], 1);
+    for (int i = 0; i < BWD_QS; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 32 * BWD_EW); mbar_init(sdp_free, 32 * BWD_EW); mbar_init(&dq_full[0], 1); mbar_init(&dq_full[1], 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
     // this thread is the TMA producer: first tiles requested before the CTA-wide set-up (see the forward)
@@ -426,9 +429,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     for (int it = 1; it < n_it; ++it) {
-      const int s = it & 1;
+      const int s = it % BWD_QS;
       const int q0 = (i_first + it) * TQ;
-      mbar_wait(&qdo_empty[s], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&qdo_empty[s], ((it / BWD_QS) & 1) ^ 1);
       mbar_arrive_expect_tx(&qdo_full[s], 2 * TILE_BYTES);
       tma_load_3d(sQ + s * TILE_BYTES, &tmQ, &qdo_full[s], h * HD, q0, b);
       tma_load_3d(sdO + s * TILE_BYTES, &tmdO, &qdo_full[s], h * HD, q0, b);
@@ -439,13 +442,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);      // dV = Pᵀ·dO, dK = dSᵀ·Q (A, B MN-major)
     constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);      // dQ = dS·K       (A K-major, B MN-major)
     const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
-    // tensor-core order once P, dS of tile `it` are published:  S, dP of tile it+1 (the elementwise warps start on them
-    // at once)  →  dQ_it  →  dV, dK of tile it.  The N = 64 MMAs read 6 KB of shared memory per 32 tensor cycles and are
+    // tensor-core order:  S, dP of tile it+1 as soon as the elementwise warps hold S, dP of tile `it` in registers
+    // (sdp_free; their wait for the previous MMAs and the 64 KB burst of P / dS stores overlaps these MMAs)  →  once
+    // P, dS are published: dQ_it  →  dV, dK of tile it.  The N = 64 MMAs read 6 KB of shared memory per 32 tensor cycles and are
     // shared-memory-bandwidth bound (~48 cycles each).
     auto issue_sdp = [&](int it) {
-      const int s = it & 1;
+      const int s = it % BWD_QS;
       const uint32_t aQ = smem_u32(sQ + s * TILE_BYTES), adO = smem_u32(sdO + s * TILE_BYTES);
-      mbar_wait(&qdo_full[s], (it >> 1) & 1);
+      mbar_wait(&qdo_full[s], (it / BWD_QS) & 1);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -462,15 +466,18 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       AT_STAMP(0, 5);
     }
     for (int it = 0; it < n_it; ++it) {
-      const int s = it & 1;
-      const uint32_t aQ = smem_u32(sQ + s * TILE_BYTES), adO = smem_u32(sdO + s * TILE_BYTES);
-      mbar_wait(pds_full, it & 1);                 // P and dS in shared memory; S, dP consumed; dQ_{it-1} drained
-      tc_fence_after();
-      AT_STAMP(it, 6);
+      const int s = it & 1;                        // dQ buffer
+      const int sq = it % BWD_QS;                  // Q / dO stage
+      const uint32_t aQ = smem_u32(sQ + sq * TILE_BYTES), adO = smem_u32(sdO + sq * TILE_BYTES);
       if (it + 1 < n_it) {
+        mbar_wait(sdp_free, it & 1);               // S, dP of tile `it` are in the elementwise warps' registers
+        tc_fence_after();
         issue_sdp(it + 1);
         AT_STAMP(it + 1, 5);
       }
+      mbar_wait(pds_full, it & 1);                 // P and dS in shared memory; dQ_{it-2} drained
+      tc_fence_after();
+      AT_STAMP(it, 6);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < TK / 16; ++k)
@@ -486,7 +493,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int k = 0; k < TQ / 16; ++k)
           umma_f16_ss(tdK, desc_mnmajor(adS, k), desc_mnmajor(aQ, k), idesc_t, (it | k) != 0);
-        umma_commit(&qdo_empty[s]);
+        umma_commit(&qdo_empty[sq]);
         umma_commit(mma_done);                     // P / dS of this tile may be overwritten
       }
       __syncwarp();
@@ -498,10 +505,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp >= 2) {
     // ===================== softmax-backward threads (thread = query row of the current tile) =====================
-    // warps 2..9: TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4.  With one warp per
+    // warps 2..17: TMEM lane quadrant = warp % 4 (hardware rule), column part = (warp - 2) / 4.  With one warp per
     // scheduler the elementwise phase was latency-bound (~10 k cycles per tile pair against 1.3 k cycles of MMA).
     const int rb = (warp & 3) * 32;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;           // which 32 of the 128 key columns
+    const int half = part & 1;                  // dQ drain / dK, dV epilogue: parts 0 and 1 only, 32 columns each
+    const bool drains = part < 2;
     const int r = rb + lane;
     const uint32_t lane_addr = (uint32_t)rb << 16;
     const float slope2 = (slopes ? slopes[h] : 0.f) * kLog2e;
@@ -522,6 +531,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // back and issued eight 16-byte vector atomics per thread — 1.3-1.7 k cycles per tile on the loop's critical path.
     // It runs one tile late (dQ is double-buffered in TMEM), in the bubble after P / dS of the next tile are published.
     auto drain_dq = [&](int t) {
+      if (!drains) return;                      // warp-uniform
       uint8_t* scr = sDQ + (warp - 2) * 4096;
       mbar_wait(&dq_full[t & 1], (t >> 1) & 1);
       tc_fence_after();
@@ -570,12 +580,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // The results stay in registers (64 columns x {P, dS} as packed bf16 pairs) until the previous tile's dQ / dV /
       // dK MMAs have finished reading P and dS from shared memory: only the short burst of stores waits for them, the
       // exponentials of this tile overlap them.
-      uint32_t pkp[32], pkd[32];
+      uint32_t pkp[16], pkd[16];
       auto pair_tile = [&](auto masked_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-        for (int cc = 0; cc < TK / 32; ++cc) {
-          const int c = half * (TK / 32) + cc;
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = part * 2 + cc;
           uint32_t vs[16], vp[16];
           tmem_ld_32x32b_x16(tS + lane_addr + c * 16, vs);
           tmem_ld_32x32b_x16(tdP + lane_addr + c * 16, vp);
@@ -602,13 +612,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       };
       if (full_pair) pair_tile(std::false_type{}); else pair_tile(std::true_type{});
       tc_fence_before();                              // S / dP of this tile are consumed
+      mbar_arrive(sdp_free);
       if (threadIdx.x == 64) AT_STAMP(it, 1);
       if (it > 0) mbar_wait(mma_done, (it - 1) & 1);  // the previous tile's MMAs no longer read P / dS
 #pragma unroll
-      for (int cc = 0; cc < TK / 32; ++cc) {
+      for (int cc = 0; cc < 2; ++cc) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const uint32_t off = sw128_piece(r, (half * (TK / 32) + cc) * 2 + g);
+          const uint32_t off = sw128_piece(r, (part * 2 + cc) * 2 + g);
           *reinterpret_cast<uint4*>(sP + off) =
               make_uint4(pkp[cc * 8 + g * 4 + 0], pkp[cc * 8 + g * 4 + 1], pkp[cc * 8 + g * 4 + 2], pkp[cc * 8 + g * 4 + 3]);
           *reinterpret_cast<uint4*>(sdS + off) =
@@ -632,7 +643,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(acc_full, 0);
       tc_fence_after();
     }
-    {
+    if (drains) {
       uint8_t* scr = sDQ + (warp - 2) * 4096;
       if (lane == 0) tma_store_wait_read<0>();        // the last dQ reduce has finished reading the scratch
       __syncwarp();
