@@ -335,6 +335,12 @@ int vg_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   vg_stream_t stream);
 int vg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vg_stream_t stream);
 
+/* Clear n_seg element ranges [seg_off[i], seg_off[i] + seg_len[i]) of one fp32 buffer in ONE launch (offsets and lengths
+ * in elements, multiples of 4; tables in device memory).  The gradient arena (vae_gslm_b200/arena.py) clears only the
+ * slices whose gradients are ACCUMULATED by autograd (torch's AccumulateGrad, training_lib/optimizer.py semantics); the
+ * big matrices are overwritten by their first weight-gradient GEMM of the step (beta = 0) instead. */
+int vg_zero_segments(float* base, const int64_t* seg_off, const int64_t* seg_len, int n_seg, vg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

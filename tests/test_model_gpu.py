@@ -215,6 +215,41 @@ def test_train_step_overlapped_graph_matches_serial_eager(golden):
     assert max_rel(p1, p0) < 1e-2
 
 
+def test_first_writer_overwrite_matches_whole_arena_clear(golden):
+    """arena.py: after the calibration step the big matrices are no longer cleared — their first weight-gradient GEMM of a
+    step overwrites (beta = 0) and vg_zero_segments clears the rest.  Two steps (so that a stale gradient would show)
+    must give the gradients and parameters of the clear-everything / accumulate-everything protocol."""
+    from vae_gslm_b200.arena import ParamArena
+    from vae_gslm_b200.dp import GradReducer
+    from vae_gslm_b200.trainers.speech.lvtr import TrainStep
+    i = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in golden["inputs"].items()}
+    batch = {k: i[k] for k in ("x", "mask", "utterance", "utt_mask")}
+    draws = {k: i[k] for k in ("eps_q", "init_state", "eps_p", "diff_t", "diff_noise")}
+    runs = []
+    for overwrite in (False, True):
+        model = build_small(golden, torch.bfloat16)
+        inner = model.forward
+        model.forward = lambda x, _f=inner, **kw: _f(x, **kw, **draws)
+        arena = ParamArena(model, weight_decay=0.1)
+        arena._BIG = 1 << 12                      # the small configuration has no 1.5 M-element matrix
+        if not overwrite:
+            arena.finish_calibration = lambda: setattr(arena, "_calibrating", False)
+        step = TrainStep(model, arena, GradReducer(arena), batch, lr=0.0, kld_weight=0.04, use_cuda_graph=False)
+        if overwrite:
+            assert len(arena._overwrite) > 10 and any(sg is not None and sg[2] > 0 for sg in arena._segments)
+            big = [p for g in arena.groups for p in g.params if id(p) in arena._overwrite and p.numel() >= arena._BIG]
+            assert big and float(big[0].grad.abs().max()) > 0
+        else:
+            assert not arena._overwrite and arena._segments is None
+        for _ in range(2):
+            loss = float(step(lr=1e-3))
+        runs.append((loss, torch.cat([g.p.detach().float().cpu() for g in arena.groups]),
+                     torch.cat([g.g.detach().float().cpu() for g in arena.groups])))
+    (l0, p0, g0), (l1, p1, g1) = runs
+    assert abs(l0 - l1) <= 2e-3 * abs(l0), (l0, l1)
+    assert max_rel(g1, g0) < 2e-2 and max_rel(p1, p0) < 1e-2
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 6e-2)])
 def test_ddim_decode_matches_reference(golden, dtype, tol):
     """LVTR.decode (DDIM, 6 steps) against the real reference's output with the same injected noises; every

@@ -158,6 +158,7 @@ _SIGNATURES = {
     "vg_masked_l1_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
     "vg_sample_token": (C.c_int, [_p, _i64, _p, _f32, _p, _i64, _i64, C.c_int, _p]),
     "vg_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _p, _p]),
+    "vg_zero_segments": (C.c_int, [_p, _p, _p, C.c_int, _p]),
     "vg_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
 }
 

@@ -92,7 +92,18 @@ class ParamArena:
         # into it directly (beta = 1) and hand autograd None, so no AccumulateGrad add kernel runs for them.
         # Gradients that still come back through autograd (torch ops, the fused latent / conv kernels) are added into
         # the same slice by autograd itself.  Both are accumulations, hence one whole-arena clear per step.
+        #
+        # After one CALIBRATION step (calibrate_next → finish_calibration) the arena knows which parameters are written
+        # ONLY through those direct sites.  From then on the first direct write of a step OVERWRITES (beta = 0), and
+        # zero_grad() clears just the remaining slices (everything autograd accumulates into, plus small direct ones)
+        # with one vg_zero_segments launch: the 0.9 GB memset and the weight-gradient GEMMs' read of C disappear.
         self.direct: List[nn.Parameter] = []
+        self._calibrating = False
+        self._direct_calls: Dict[int, int] = {}
+        self._autograd_hits: Dict[int, int] = {}
+        self._overwrite: set = set()          # id(param): first direct write of a step uses beta = 0
+        self._written: set = set()
+        self._segments: Optional[List[Optional[Tuple[torch.Tensor, torch.Tensor, int]]]] = None
         if direct_wgrad:
             for grp in self.groups:
                 for p in grp.params:
@@ -100,14 +111,79 @@ class ParamArena:
                     p._vg_arena = self
                     self.direct.append(p)
 
+    # ------------------------------------------------------------------ calibration of the overwrite set
+    # elements.  Smaller slices are simply cleared (one launch clears all of them).  1.5 M keeps the [1024, 1024] output
+    # projections on the accumulate path: their weight-gradient GEMMs run split-K (red.global.add into C), which
+    # would need its own clear of C for beta = 0.
+    _BIG = 3 << 19
+
+    def calibrate_next(self) -> None:
+        """observe, during the next step, which parameters receive their gradient only through wgrad_beta() sites.
+        Tensor hooks see the gradient autograd is about to accumulate — None when an op wrote the slice itself (torch
+        calls tensor and post-accumulate hooks for undefined gradients too, so the VALUE has to be looked at)."""
+        self._calibrating = True
+        self._direct_calls, self._autograd_hits = {}, {}
+        self._overwrite, self._segments = set(), None
+
+        def seen(g, i):
+            if g is not None:
+                self._autograd_hits[i] = self._autograd_hits.get(i, 0) + 1
+
+        self._cal_handles = [p.register_hook(lambda g, i=id(p): seen(g, i)) for p in self.direct]
+
+    def finish_calibration(self) -> None:
+        self._calibrating = False
+        for h in getattr(self, "_cal_handles", []):
+            h.remove()
+        self._cal_handles = []
+        self._overwrite = {i for i, n in self._direct_calls.items() if n > 0 and self._autograd_hits.get(i, 0) == 0}
+        segments = []
+        for grp in self.groups:
+            runs: List[List[int]] = []          # [offset, length] in elements, merged
+            for k, (p, o) in enumerate(zip(grp.params, grp.offsets)):
+                end = grp.offsets[k + 1] if k + 1 < len(grp.offsets) else grp.numel
+                if id(p) in self._overwrite and p.numel() >= self._BIG:
+                    continue
+                if runs and runs[-1][0] + runs[-1][1] == o:
+                    runs[-1][1] = end - runs[-1][0]
+                else:
+                    runs.append([o, end - o])
+            total = sum(r[1] for r in runs)
+            if not runs:
+                segments.append((None, None, 0))
+            elif total * 2 > grp.numel or len(runs) > 4096:
+                segments.append(None)                                  # not worth it: whole-arena clear
+            else:
+                dev = grp.g.device
+                segments.append((torch.tensor([r[0] for r in runs], dtype=torch.int64, device=dev),
+                                 torch.tensor([r[1] for r in runs], dtype=torch.int64, device=dev), len(runs)))
+        self._segments = segments
+
     # ------------------------------------------------------------------ per-step protocol
     def zero_grad(self) -> None:
-        """one memset per arena (0.9 GB at HBM speed ≈ 0.15 ms); every producer accumulates afterwards."""
-        for grp in self.groups:
-            grp.g.zero_()
+        """clear what is accumulated into: the whole arena (0.9 GB at HBM speed ≈ 0.15 ms) before calibration, afterwards
+        only the slices outside the overwrite set."""
+        for gi, grp in enumerate(self.groups):
+            seg = self._segments[gi] if self._segments is not None else None
+            if seg is None:
+                grp.g.zero_()
+            elif seg[2] > 0:
+                L.call("vg_zero_segments", L.ptr(grp.g), L.ptr(seg[0]), L.ptr(seg[1]), seg[2], L.stream())
+        self._written = set()
         self.micro_batch = 0
 
-    def wgrad_beta(self) -> float:
+    def wgrad_beta(self, param: Optional[nn.Parameter] = None) -> float:
+        """beta of a direct gradient write into ``param``'s slice: 0 for the first write of a step into a parameter of
+        the overwrite set (its slice was not cleared), 1 otherwise."""
+        if param is None:
+            return 1.0
+        i = id(param)
+        if self._calibrating:
+            self._direct_calls[i] = self._direct_calls.get(i, 0) + 1
+            return 1.0
+        if i in self._overwrite and param.numel() >= self._BIG and i not in self._written:
+            self._written.add(i)
+            return 0.0
         return 1.0
 
     def end_micro_batch(self) -> None:

@@ -71,6 +71,16 @@ cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
   }
 }
 
+// zero a list of [offset, offset + length) element ranges of one fp32 buffer (offsets / lengths multiples of 4):
+// blockIdx.y = range, blockIdx.x strides over it
+__global__ void zero_segments_kernel(float* __restrict__ base, const int64_t* __restrict__ seg_off,
+                                     const int64_t* __restrict__ seg_len) {
+  float4* p = reinterpret_cast<float4*>(base + seg_off[blockIdx.y]);
+  const int64_t n4 = seg_len[blockIdx.y] / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 }  // namespace vg
 
 using namespace vg;
@@ -89,6 +99,16 @@ extern "C" int vg_adamw_step(float* param, const float* grad, float* exp_avg, fl
       param, grad, exp_avg, exp_avg_sq, (__nv_bfloat16*)shadow_bf16, n, lr, beta1, beta2, eps,
       1.f - lr * weight_decay, 1.f / bias_corr1, 1.f / sqrtf(bias_corr2), grad_scale, hyper_dev);
   VG_LAUNCH_CHECK("vg_adamw_step");
+  return 0;
+}
+
+extern "C" int vg_zero_segments(float* base, const int64_t* seg_off, const int64_t* seg_len, int n_seg,
+                                vg_stream_t stream) {
+  VG_REQUIRE(base && seg_off && seg_len, -1, "vg_zero_segments: null pointer");
+  VG_REQUIRE(n_seg > 0 && n_seg <= 65535, -3, "vg_zero_segments: 1..65535 segments");
+  VG_REQUIRE(aligned(base, 16), -4, "vg_zero_segments: base must be 16-byte aligned");
+  zero_segments_kernel<<<dim3(64, (unsigned)n_seg), 256, 0, (cudaStream_t)stream>>>(base, seg_off, seg_len);
+  VG_LAUNCH_CHECK("vg_zero_segments");
   return 0;
 }
 

@@ -180,7 +180,7 @@ def _bgrad(dy2: torch.Tensor, bias: torch.Tensor) -> Optional[torch.Tensor]:
     if main is not None:
         arena = bias._vg_arena
         with _on_grad_stream(dy2):
-            colsum(dy2, out=main, beta=arena.wgrad_beta())
+            colsum(dy2, out=main, beta=arena.wgrad_beta(bias))
             arena.grad_ready(bias)
         return None
     return colsum(dy2)
@@ -263,7 +263,7 @@ class _RMSNorm(torch.autograd.Function):
         scale = ctx.scale_param
         main = getattr(scale, "_vg_main_grad", None)
         if main is not None:
-            dscale, beta = main, scale._vg_arena.wgrad_beta()
+            dscale, beta = main, scale._vg_arena.wgrad_beta(scale)
         else:
             dscale, beta = torch.empty(dim, dtype=torch.float32, device=x2.device), 0.0
         ws = L.workspace(L.load().vg_rmsnorm_bwd_workspace(rows, dim), x2.device)
@@ -295,7 +295,7 @@ def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor) -> Optiona
     if main is not None:
         arena = weight._vg_arena
         with _on_grad_stream(dy2, x2):
-            gemm(dy2, x2, trans_a=True, trans_b=False, out=main.view(main.shape[0], -1), beta=arena.wgrad_beta())
+            gemm(dy2, x2, trans_a=True, trans_b=False, out=main.view(main.shape[0], -1), beta=arena.wgrad_beta(weight))
             arena.grad_ready(weight)
         return None
     dw = gemm(dy2, x2, trans_a=True, trans_b=False, out_dtype=torch.float32).view(weight.shape)   # 1x1 conv: [N,K,1]

@@ -79,7 +79,11 @@ class TrainStep:
         n0 = _lib.launch_count
         if hasattr(self.reducer, "calibrate_next"):
             self.reducer.calibrate_next()                   # first step: learn how often each gradient is announced
+        if hasattr(self.arena, "calibrate_next"):
+            self.arena.calibrate_next()                     # … and which gradients are only ever written directly
         self._run_eager(device_hyper=False)                 # also the first warm-up iteration
+        if hasattr(self.arena, "finish_calibration"):
+            self.arena.finish_calibration()
         self.launches_per_step = _lib.launch_count - n0     # libvgslm kernels per step (bench.py's gpu_launches)
         if use_cuda_graph:
             try:
