@@ -434,6 +434,49 @@ def test_full_config_against_oracle(mode):
     assert not bad, bad[:20]
 
 
+def test_full_size_properties():
+    """BASELINE configs[1] size — the full model on 8 x 1000 frames in bf16 — through properties that do not need the
+    oracle at that size: padded rows are zero, what lies beyond a sequence's length or in a frame's future does not
+    reach it (causal convolutions, causal attention, row-wise GEMMs: bit-exact), and sequences do not see each other
+    (a permuted batch gives the permuted result, bit-exact)."""
+    B, T = 8, 1000
+    model, cfg, batch, rng = _full_model_and_batch(B, T)
+    model.set_compute_dtype(torch.bfloat16)
+    keys = ("transformer_latent", "log_p", "log_q", "sample_q")
+
+    def run(b, r):
+        with torch.no_grad():
+            out = model(TensorMask(b["x"], b["mask"]), utterance=TensorMask(b["utterance"], b["utt_mask"]), **r)
+        return {k: (out[k].value if hasattr(out[k], "value") else out[k]).float() for k in keys + ("logits",)}
+
+    base = run(batch, rng)
+    mask = batch["mask"]
+    assert (~mask).any()
+    for k in keys:
+        assert float(base[k][~mask].abs().max()) == 0.0, k
+        assert bool(torch.isfinite(base[k]).all()), k
+    # (1) garbage beyond the lengths, and a different future for sequence 0 (full length) after frame 600
+    t0 = 600
+    b2 = {k: v.clone() for k, v in batch.items()}
+    junk = torch.randn_like(b2["x"])
+    junk[..., 0] = torch.randint(0, 200, junk.shape[:2], device=junk.device).float()
+    b2["x"] = torch.where(mask[..., None], b2["x"], junk)
+    b2["x"][0, t0:] = junk[0, t0:]
+    r2 = {k: v.clone() for k, v in rng.items()}
+    r2["eps_q"][0, t0:] = torch.randn_like(r2["eps_q"][0, t0:])
+    got = run(b2, r2)
+    keep = mask.clone()
+    keep[0, t0:] = False
+    for k in keys + ("logits",):
+        assert torch.equal(got[k][keep], base[k][keep]), k
+    assert not torch.equal(got["transformer_latent"][0, t0 + 1:], base["transformer_latent"][0, t0 + 1:])
+    # (2) batch permutation
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4], device=mask.device)
+    got = run({k: v[perm] for k, v in batch.items()}, {k: v[perm] for k, v in rng.items()})
+    for k in keys + ("logits",):
+        assert torch.equal(got[k], base[k][perm]), k
+
+
 def test_cuda_graph_decode_matches_eager(golden):
     """the graphed single-token step (device-resident cache position) reproduces the eager loop bit for bit
     under greedy decoding with the prior noise switched off (temperature 0)."""
