@@ -53,6 +53,68 @@ def test_arena_layout(golden):
     assert sum(p.dim() == 1 for p in arena.direct) >= 2
 
 
+def test_arena_overwrite_calibration():
+    """arena.py's first-writer-overwrite protocol, host side: a parameter written ONLY by direct sites (autograd sees
+    None) joins the overwrite set, one that autograd accumulates into does not; the clear segments cover everything but
+    the big overwrite slices; beta is 0 exactly once per step for those."""
+    from vae_gslm_b200.arena import ParamArena
+
+    class Direct(torch.autograd.Function):          # what ops._wgrad does: write the slice itself, hand autograd None
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.save_for_backward(x, w)
+            ctx.w = w
+            return x @ w.t()
+
+        @staticmethod
+        def backward(ctx, g):
+            x, w = ctx.saved_tensors
+            beta = ctx.w._vg_arena.wgrad_beta(ctx.w)
+            ctx.w._vg_main_grad.mul_(beta).add_(g.t() @ x)
+            return g @ w, None
+
+    model = torch.nn.ModuleDict({"a": torch.nn.Linear(64, 256), "b": torch.nn.Linear(256, 16), "c": torch.nn.Linear(16, 8)})
+    arena = ParamArena(model, bf16_shadow=False)
+    arena._BIG = 1024
+    wa, wb = model["a"].weight, model["b"].weight
+    x = torch.randn(5, 64)
+
+    def step():
+        h = Direct.apply(x, wa)                                     # direct write
+        h = torch.nn.functional.linear(h, wb, model["b"].bias)      # autograd accumulation
+        model["c"](h).sum().backward()
+
+    arena.calibrate_next()
+    step()
+    arena.finish_calibration()
+    assert id(wa) in arena._overwrite and id(wb) not in arena._overwrite and not arena._cal_handles
+    segs = arena._segments
+    assert segs is not None
+    cleared = torch.zeros(arena.decay.numel, dtype=torch.bool)
+    off, ln, n = segs[0]
+    for o, l in zip(off.tolist(), ln.tolist()):
+        cleared[o:o + l] = True
+    where = {id(p): k for k, p in enumerate(arena.decay.params)}
+    oa, na = arena.decay.slice_of(where[id(wa)])
+    ob, nb = arena.decay.slice_of(where[id(wb)])
+    assert not cleared[oa:oa + na].any() and cleared[ob:ob + nb].all() and n == len(off)
+    # per-step protocol (zero_grad itself needs the CUDA library: emulate it)
+    expect = None
+    for it in range(2):
+        arena._written = set()
+        for o, l in zip(off.tolist(), ln.tolist()):
+            arena.decay.g[o:o + l] = 0
+        arena.nodecay.g.zero_()
+        step()
+        ga = wa.grad.clone()
+        if expect is None:
+            expect = ga
+        assert torch.allclose(ga, expect, rtol=1e-6, atol=1e-6)       # no stale gradient survives un-cleared slices
+    assert arena.wgrad_beta(wa) == 1.0 and arena.wgrad_beta(wb) == 1.0   # already written this step / not in the set
+    arena._written = set()
+    assert arena.wgrad_beta(wa) == 0.0 and arena.wgrad_beta(wa) == 1.0
+
+
 def _worker(rank, world, port, fixture_path, result_q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
