@@ -53,6 +53,39 @@ def test_arena_layout(golden):
     assert sum(p.dim() == 1 for p in arena.direct) >= 2
 
 
+def test_compact_checkpoint_roundtrip_and_resume(golden, tmp_path):
+    """trainers/speech/lvtr.py save_checkpoint / load_checkpoint: the reference's compact format (state_dict under
+    last-cpt.ckpt + hp.yaml, inference/inferer.py:17-28) plus the arena's AdamW state for resuming."""
+    from vae_gslm_b200.hparams.hp import Hparams
+    from vae_gslm_b200.trainers.speech.lvtr import load_checkpoint, save_checkpoint
+    model, arena = _build(golden)
+    hp = Hparams.from_dict({"model": copy.deepcopy(golden["config"])})
+    torch.manual_seed(0)
+    for grp in arena.groups:
+        grp.m.normal_()
+        grp.v.uniform_()
+    arena.step_count = 17
+    save_checkpoint(model, hp, str(tmp_path), arena=arena, global_step=1234)
+    on_disk = torch.load(tmp_path / "last-cpt.ckpt", weights_only=True)
+    # (the golden fixture holds the trainable tensors; the file also has the diffusion schedule buffers, as the reference's)
+    assert set(on_disk) == set(model.state_dict()) and set(on_disk) >= set(golden["state_dict"])
+    assert all(torch.equal(on_disk[k], v) for k, v in golden["state_dict"].items())
+    assert Hparams.from_yamlfile(str(tmp_path / "hp.yaml")) == hp
+    model2, arena2 = _build(golden)
+    with torch.no_grad():
+        for p in model2.parameters():
+            p.add_(1.0)
+    assert load_checkpoint(model2, str(tmp_path), arena=arena2) == 1234 and arena2.step_count == 17
+    for g1, g2 in zip(arena.groups, arena2.groups):
+        assert torch.equal(g1.p, g2.p)
+        for p, o in zip(g1.params, g1.offsets):          # (alignment gaps between slices are not state)
+            sl = slice(o, o + p.numel())
+            assert torch.equal(g1.m[sl], g2.m[sl]) and torch.equal(g1.v[sl], g2.v[sl])
+    # parameters still alias the arena after loading
+    p0 = next(model2.parameters())
+    assert p0.data_ptr() in {g.p.data_ptr() + 4 * o for g in arena2.groups for o in g.offsets}
+
+
 def test_arena_overwrite_calibration():
     """arena.py's first-writer-overwrite protocol, host side: a parameter written ONLY by direct sites (autograd sees
     None) joins the overwrite set, one that autograd accumulates into does not; the clear segments cover everything but

@@ -256,6 +256,34 @@ class ParamArena:
     def total_numel(self) -> int:
         return sum(g.numel for g in self.groups)
 
+    # ------------------------------------------------------------------ resume
+    def optimizer_state_dict(self) -> Dict[str, object]:
+        """AdamW state keyed by PARAMETER NAME (exp_avg / exp_avg_sq as tensors of the parameter's shape, like
+        ``torch.optim.AdamW.state_dict()['state']`` entries) + the step count, so that it survives a change of arena
+        layout (bucket order, alignment).  The parameters themselves are in ``model.state_dict()``."""
+        state = {}
+        for grp in self.groups:
+            for name, p, o in zip(grp.names, grp.params, grp.offsets):
+                n = p.numel()
+                state[name] = {"exp_avg": grp.m[o:o + n].view(p.shape).detach().cpu().clone(),
+                               "exp_avg_sq": grp.v[o:o + n].view(p.shape).detach().cpu().clone()}
+        return {"step": self.step_count, "state": state}
+
+    def load_optimizer_state_dict(self, sd: Dict[str, object]) -> None:
+        self.step_count = int(sd["step"])
+        for grp in self.groups:
+            for name, p, o in zip(grp.names, grp.params, grp.offsets):
+                n = p.numel()
+                st = sd["state"][name]
+                grp.m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                grp.v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+
+    def refresh_shadow(self) -> None:
+        """re-derive the bf16 weight shadows after parameters were loaded into the arena (model.load_state_dict)."""
+        for grp in self.groups:
+            if grp.shadow is not None:
+                L.call("vg_cast_f32_to_bf16", L.ptr(grp.p), L.ptr(grp.shadow), grp.numel, L.stream())
+
 
 def cosine_lr(step: int, base_lr: float, min_lr: float, flat_steps: int, total_steps: int) -> float:
     """training_lib/optimizer.py:58-107 for the VAE-GSLM recipe: flat for `flat_steps`, then cosine to min_lr."""

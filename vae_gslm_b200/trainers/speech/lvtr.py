@@ -40,6 +40,37 @@ def assemble_loss(output: Mapping, kld_weight, rec_loss_scale: float = 1.0, entr
             "length": output["log_p"].mask.sum()}
 
 
+def save_checkpoint(model, hp, directory: str, name: str = "last-cpt.ckpt", arena=None, global_step: Optional[int] = None) -> None:
+    """the reference's COMPACT checkpoint (:294-296; training_lib/callbacks.py): ``model.state_dict()`` under ``name`` and
+    the configuration as ``hp.yaml`` in ``directory`` — what ``inference/inferer.py:17-28`` and ``load_checkpoint`` read.
+    With ``arena`` the AdamW moments and step go to ``<name>.optim`` next to it, for resuming."""
+    import os
+    os.makedirs(directory, exist_ok=True)
+    torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, os.path.join(directory, name))
+    hp.save(os.path.join(directory, "hp.yaml"))
+    if arena is not None:
+        extra = arena.optimizer_state_dict()
+        extra["global_step"] = global_step
+        torch.save(extra, os.path.join(directory, name + ".optim"))
+
+
+def load_checkpoint(model, directory: str, name: str = "last-cpt.ckpt", arena=None) -> Optional[int]:
+    """load a compact checkpoint (ours or the reference's: same key names) into ``model``; with ``arena`` also the
+    optimizer state if ``<name>.optim`` exists.  Returns the stored global step (None for a reference checkpoint)."""
+    import os
+    model.load_state_dict(torch.load(os.path.join(directory, name), map_location="cpu", weights_only=True), strict=False)
+    step = None
+    if arena is not None:
+        if arena.groups[0].shadow is not None:
+            arena.refresh_shadow()
+        opt = os.path.join(directory, name + ".optim")
+        if os.path.exists(opt):
+            extra = torch.load(opt, map_location="cpu", weights_only=True)
+            arena.load_optimizer_state_dict(extra)
+            step = extra.get("global_step")
+    return step
+
+
 def make_model_input(tokens: TensorMask, mel: TensorMask) -> TensorMask:
     """channel-interleaved model input [B,T,1+n_mels]: token id as float ⊕ mel (:117-118)."""
     return TensorMask(tokens.value.to(mel.value.dtype), tokens.mask).expand().cat(mel)
