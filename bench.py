@@ -137,7 +137,9 @@ def run_ours(args):
     model.apply(init_weights)
     model = model.to(dev).set_compute_dtype(torch.bfloat16)
     arena = ParamArena(model, weight_decay=hp.training.optimizer.weight_decay)
-    reducer = GradReducer(arena, bucket_bytes=64 << 20)
+    # VG_DP_BF16=1: opt-in bf16 staging of the gradient all-reduce (dp.py); off = the reference's fp32 DDP reduction
+    dp_bf16 = world > 1 and os.environ.get("VG_DP_BF16", "0") == "1"
+    reducer = GradReducer(arena, bucket_bytes=64 << 20, compress_bf16=dp_bf16)
     lr = hp.training.optimizer.lr
 
     host = synthetic_batch(B, T, rank, pin=True)
@@ -215,7 +217,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"VAE-GSLM bf16 training step (fwd+bwd+allreduce+AdamW), {T / 50:.0f} s segments",
-                   "per_gpu_batch": B, "frames_per_seq": T, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "per_gpu_batch": B, "frames_per_seq": T, "global_batch": B * world, "parallelism": f"dp{world}" + ("+bf16-grad-allreduce" if dp_bf16 else ""),
                    "params": 226_957_564, "l2": "working set (454 MB bf16 weights + activations) exceeds the 126 MB L2",
                    "init": "random (reference init rules)"},
         "per_gpu_frames_per_sec": round(value / world, 1),

@@ -148,14 +148,14 @@ def test_arena_overwrite_calibration():
     assert arena.wgrad_beta(wa) == 0.0 and arena.wgrad_beta(wa) == 1.0
 
 
-def _worker(rank, world, port, fixture_path, result_q):
+def _worker(rank, world, port, fixture_path, result_q, compress=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from vae_gslm_b200.dp import GradReducer
         golden = torch.load(fixture_path, map_location="cpu", weights_only=False)
         model, arena = _build(golden)
-        reducer = GradReducer(arena, bucket_bytes=1 << 16)
+        reducer = GradReducer(arena, bucket_bytes=1 << 16, compress_bf16=compress)
         params = list(model.parameters())
 
         def backward(scale):
@@ -184,12 +184,13 @@ def _worker(rank, world, port, fixture_path, result_q):
         dist.destroy_process_group()
 
 
-def test_grad_reducer_world2_gloo(golden, tmp_path):
+@pytest.mark.parametrize("compress", [False, True])
+def test_grad_reducer_world2_gloo(golden, tmp_path, compress):
     fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lvtr_small.pt")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, fixture, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, fixture, q, compress)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=180) for _ in procs]
