@@ -122,3 +122,27 @@ def test_train_batches_rotate_slots(tmp_path):
     for b in seen:
         assert set(b) == {"x", "mask", "utterance", "utt_mask"} and b["x"].shape == (3, 64, 1 + N_MELS)
         assert bool(b["mask"].any(1).all()) and bool((b["x"][~b["mask"]] == 0).all())
+
+
+def test_train_batches_shard_by_rank(tmp_path):
+    """two ranks see disjoint halves of the epoch (torch DistributedSampler, as the reference's StandardSampler) and
+    every rank draws the same permutation for the same epoch."""
+    cfg, mel, hubert, rescale = _corpus(tmp_path, n=8)
+    cfg.pop("random_crop_mel_utt")                     # deterministic items: identify utterances by their content
+    cfg["random_crop_mel"] = {"min_seg_sec": 100.0, "max_seg_sec": 100.0}      # crop longer than any file = identity
+    ds = TokenMelDataset(Hparams.from_dict(cfg), Hparams.from_dict(mel), Hparams.from_dict(hubert), Hparams.from_dict(rescale))
+    n = len(ds)
+    seen = []
+    for rank in range(2):
+        torch.manual_seed(0)
+        asm = BatchAssembler(1, 64, 512, N_MELS, pin=False)
+        firsts = [float(b["utterance"][0, 0, 0]) for b in
+                  train_batches(ds, asm, 1, shuffle=True, seed=5, rank=rank, world_size=2, epoch=3, utt_key="cropped_mel")]
+        assert len(firsts) == n // 2
+        seen.append(firsts)
+    assert not set(seen[0]) & set(seen[1]) and len(set(seen[0]) | set(seen[1])) == 2 * (n // 2)
+    want = torch.utils.data.distributed.DistributedSampler(ds, num_replicas=2, rank=0, shuffle=True, seed=5, drop_last=True)
+    want.set_epoch(3)
+    first_of = {i: float(((torch.from_numpy(__import__("numpy").load(ds.mel_path(i))) - rescale["mean"]) / rescale["std"])[0, 0])
+                for i in range(n)}
+    assert seen[0] == [pytest.approx(first_of[i]) for i in want]

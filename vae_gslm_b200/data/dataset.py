@@ -216,12 +216,23 @@ class BatchAssembler:
 
 
 def train_batches(dataset: TokenMelDataset, assembler: BatchAssembler, batch_size: int, shuffle: bool = True,
-                  num_workers: int = 0, seed: int = 0, drop_last: bool = True):
+                  num_workers: int = 0, seed: int = 0, drop_last: bool = True, rank: Optional[int] = None,
+                  world_size: Optional[int] = None, epoch: int = 0, utt_key: str = "cropped_mel_utt"):
     """iterate pinned, assembled batches (keys match ``TrainStep.static``): items are read and cropped by
     ``num_workers`` DataLoader workers, the interleaved layout is written once, in the parent, into the rotating pinned
-    slots — ``step.load(batch)`` then issues the asynchronous H2D copies."""
-    g = torch.Generator().manual_seed(seed)
-    loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=shuffle, num_workers=num_workers,
-                                         collate_fn=list, drop_last=drop_last, generator=g)
+    slots — ``step.load(batch)`` then issues the asynchronous H2D copies.  With ``rank`` / ``world_size`` the epoch is
+    sharded by torch's ``DistributedSampler`` exactly as the reference's ``StandardSampler(distributed=True)`` does
+    (data/sampler.py:9-24, training_lib/trainer.py:52-65): pass the epoch number so that every rank reshuffles alike."""
+    if rank is not None:
+        assert world_size is not None
+        sampler = torch.utils.data.distributed.DistributedSampler(dataset, num_replicas=world_size, rank=rank,
+                                                                  shuffle=shuffle, seed=seed, drop_last=drop_last)
+        sampler.set_epoch(epoch)
+        loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, sampler=sampler, num_workers=num_workers,
+                                             collate_fn=list, drop_last=drop_last)
+    else:
+        g = torch.Generator().manual_seed(seed + epoch)
+        loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=shuffle, num_workers=num_workers,
+                                             collate_fn=list, drop_last=drop_last, generator=g)
     for items in loader:
-        yield assembler(items)
+        yield assembler(items, utt_key=utt_key)
