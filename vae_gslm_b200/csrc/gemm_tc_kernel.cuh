@@ -1,6 +1,9 @@
 // gemm_tc_kernel.cuh — the tcgen05 bf16 GEMM kernel template (see gemm_tc.cu for the overview).  Included by the
 // per-operand-layout translation units gemm_tc_{kk,kmn,mnk,mnmn}.cu so that they compile in parallel.
 #pragma once
+#ifndef VG_GEMM_UNIFORM_ISSUE
+#define VG_GEMM_UNIFORM_ISSUE 0
+#endif
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "sm100.cuh"
@@ -394,7 +397,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_units = num_m * num_n * epi.splits;
   const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
 
-  if (warp == 0 && lane == 0) {
+  // VG_GEMM_UNIFORM_ISSUE (compile-time, default 0): the producer / MMA-issuer warps walk their loops as whole warps and
+  // one elect.sync-elected lane issues.  Inside a `lane == 0` branch the compiler wraps every TMA / tcgen05.mma in a
+  // per-thread ELECT / R2UR / BRA.U.ANY loop (~80 cycles per instruction: measured in the attention kernels, where the
+  // same change made the MMAs issue back to back — profiles/r01_attention_v2.md); with 128-wide tiles (64 tensor cycles
+  // per MMA) that is issue-bound.  Prepared, not yet measured on the GEMM: the default build is unchanged.
+  constexpr bool kUniformIssue = VG_GEMM_UNIFORM_ISSUE != 0;
+  if (warp == 0 && (kUniformIssue || lane == 0)) {
     // ===================== TMA producer (every CTA loads its own A rows and its own slice of B) =====================
     int s = 0;
     uint32_t ph = 0;
@@ -407,6 +416,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* a_dst = smem + s * Cfg::kStageBytes;
         uint8_t* b_dst = a_dst + A_TILE_BYTES;
         const int k0 = kb * TBK;
+        if (!kUniformIssue || elect_one()) {
         if constexpr (CTAS == 2) {
           // both CTAs' bytes are counted on the LEADER's barrier (the MMA issuer lives there)
           const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
@@ -438,10 +448,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < BNL / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + 64 * j, k0);
           }
         }
+        }
+        if (kUniformIssue) __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+  } else if (warp == 1 && (kUniformIssue || lane == 0) && cta_rank == 0) {
     // ===================== MMA issuer (the leader CTA issues for the pair) =====================
     constexpr uint32_t idesc = make_idesc_bf16(TBM * CTAS, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int s = 0;
@@ -459,6 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
         const uint32_t b_addr = a_addr + A_TILE_BYTES;
+        if (!kUniformIssue || elect_one()) {
 #pragma unroll
         for (int k = 0; k < TBK / 16; ++k) {
           // K-major  : rows at 128 B pitch, 8-row groups every 1024 B (SBO); +32 B per 16-wide k step.
@@ -472,10 +485,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // frees the smem slot (in both CTAs) once these MMAs retire
         if constexpr (CTAS == 2) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+        if (kUniformIssue && kb + 1 == w.kb1) {      // same lane as the MMAs it tracks
+          if constexpr (CTAS == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+        }
+        }
+        if (kUniformIssue) __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
       // accumulator complete → epilogue warps (of both CTAs)
-      if constexpr (CTAS == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+      if (!kUniformIssue || (w.kb0 >= w.kb1 && elect_one())) {
+        if constexpr (CTAS == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+      }
+      if (kUniformIssue) __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1u;
     }
