@@ -40,6 +40,19 @@ struct DlParams {
   int B, N, K, Nc, KL, ksplit, Bp, ksub;
   unsigned long long* trace;          // debug: per-phase clock64 stamps of CTA 0 (vg_debug_decode_linear_trace)
 };
+#ifndef VG_DL_UNIFORM_ISSUE
+#define VG_DL_UNIFORM_ISSUE 0
+#endif
+#if VG_DL_UNIFORM_ISSUE
+__device__ __forceinline__ bool dl_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+#define DL_ISSUER() (dl_elect_one())
+#else
+#define DL_ISSUER() (lane == 0)
+#endif
 #define DL_STAMP(i) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[i] = clock64(); } while (0)
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -154,7 +167,10 @@ decode_linear_kernel(const __grid_constant__ DlParams p) {
   const int w_rows = min(Nc, p.N - n0);
   if (tid == 0) dl_mbar_expect_tx(&bars[0], (uint32_t)w_rows * row_bytes);
   __syncthreads();
-  if (lane == 0)
+  // -DVG_DL_UNIFORM_ISSUE=1 (experiment, default off): elect.sync in warp-uniform code instead of a `lane == 0` branch, in
+  // which the compiler wraps every UBLKCP in a per-thread ELECT / R2UR loop — the ~55 cycles per copy measured above
+  // (same effect and fix as for tcgen05.mma in attn_tc.cu; not yet measured here)
+  if (DL_ISSUER())
     for (int row = warp; row < w_rows; row += DL_WARPS)
       bulk_g2s(Wsm + (size_t)row * KLP, p.W + (int64_t)(n0 + row) * p.ldw + k0, row_bytes, &bars[0]);
   DL_STAMP(1);
@@ -162,7 +178,7 @@ decode_linear_kernel(const __grid_constant__ DlParams p) {
   pdl_wait();
   DL_STAMP(2);
   if (tid == 0) dl_mbar_expect_tx(&bars[1], (uint32_t)p.B * row_bytes);     // (bars[1] is only waited on below)
-  if (lane == 0) {
+  if (DL_ISSUER()) {
     // the expect_tx above must precede the copies' complete_tx only in the sense that the phase cannot complete
     // before both happened: the pending arrival count (1) is consumed by that expect_tx arrive
     for (int row = warp; row < p.B; row += DL_WARPS)
