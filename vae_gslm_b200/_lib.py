@@ -13,7 +13,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvgslm.so")
+# VGSLM_LIB: path of an alternative build of the same library (A/B runs of experiment switches, tools/build_variant.sh)
+LIB_PATH = os.environ.get("VGSLM_LIB") or os.path.join(_HERE, "libvgslm.so")
 
 VG_F32, VG_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU, ACT_MULT = 0, 1, 2, 3, 4
