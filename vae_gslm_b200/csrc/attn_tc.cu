@@ -353,6 +353,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 64) AT_MARK(4);
 }
 
+#if defined(VG_ATTN_FWD_SPLIT) && VG_ATTN_FWD_SPLIT == 2
+#include "attn_tc_fwd_split.cuh"
+#endif
+
 // =========================================================================================== backward
 constexpr int BWD_EW = 16;                  // elementwise warps: four per TMEM lane quadrant, 32 of the 128 key columns each
 constexpr int BWD_THREADS = 64 + 32 * BWD_EW;      // + TMA producer warp + MMA issuer warp
@@ -742,14 +746,22 @@ int attn_tc_fwd_launch(const void* q, const void* k, const void* v, int64_t ld_q
   if ((rc = make_tmap_bf16_3d(&tmV, v, (int64_t)H * HD, Tk, B, ld_kv, (int64_t)Tk * ld_kv, HD, TK))) return rc;
   CUtensorMap tmO;           // output rows leave as one [32 x 64] box per warp
   if ((rc = make_tmap_bf16_3d(&tmO, out, (int64_t)H * HD, Tq, B, ld_out, (int64_t)Tq * ld_out, HD, 32))) return rc;
+  AttnTcShape sh{B, H, Tq, Tk, q_offset, scale, g_attn_trace};
+  dim3 grid((unsigned)((Tq + TQ - 1) / TQ) * (unsigned)H * (unsigned)B);
   static bool set = false;
+#if defined(VG_ATTN_FWD_SPLIT) && VG_ATTN_FWD_SPLIT == 2
+  if (!set) {
+    VG_CUDA(cudaFuncSetAttribute(attn_tc_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWDS_SMEM));
+    set = true;
+  }
+  attn_tc_fwd_split_kernel<<<grid, FWDS_THREADS, FWDS_SMEM, st>>>(tmQ, tmK, tmV, tmO, lse, kv_len, slopes, sh);
+#else
   if (!set) {
     VG_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     set = true;
   }
-  AttnTcShape sh{B, H, Tq, Tk, q_offset, scale, g_attn_trace};
-  dim3 grid((unsigned)((Tq + TQ - 1) / TQ) * (unsigned)H * (unsigned)B);
   attn_tc_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, tmO, lse, kv_len, slopes, sh);
+#endif
   VG_LAUNCH_CHECK("vg_attn_fwd(tcgen05)");
   return 0;
 }
