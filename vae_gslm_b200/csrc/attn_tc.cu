@@ -689,6 +689,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 64) AT_MARK(4);
 }
 
+#if defined(VG_ATTN_BWD_PERSIST) && VG_ATTN_BWD_PERSIST
+#include "attn_tc_bwd_persist.cuh"
+#endif
+
 // delta[b,h,i] = Σ_d dO[i,d]·O[i,d]   (bf16 inputs)
 __global__ void attn_tc_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld_dout,
                                      const __nv_bfloat16* __restrict__ out, int64_t ld_out, float* __restrict__ delta,
@@ -794,15 +798,29 @@ int attn_tc_bwd_launch(const void* dout, int64_t ld_dout, const void* q, const v
   CUtensorMap tmDK, tmDV;    // dK / dV rows leave as [32 x 64] boxes
   if ((rc = make_tmap_bf16_3d(&tmDK, dk, (int64_t)H * HD, Tk, B, ld_dkv, (int64_t)Tk * ld_dkv, HD, 32))) return rc;
   if ((rc = make_tmap_bf16_3d(&tmDV, dv, (int64_t)H * HD, Tk, B, ld_dkv, (int64_t)Tk * ld_dkv, HD, 32))) return rc;
+  AttnTcShape sh{B, H, Tq, Tk, q_offset, scale, g_attn_trace};
   static bool set = false;
+#if defined(VG_ATTN_BWD_PERSIST) && VG_ATTN_BWD_PERSIST
+  static int sms = 0;
+  if (!set) {
+    int dev = 0;
+    VG_CUDA(cudaGetDevice(&dev));
+    VG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    VG_CUDA(cudaFuncSetAttribute(attn_tc_bwd_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    set = true;
+  }
+  const int n_items = ((Tk + TK - 1) / TK) * H * B;
+  attn_tc_bwd_persist_kernel<<<(unsigned)(n_items < sms ? n_items : sms), BWD_THREADS, BWD_SMEM, st>>>(
+      tmQ, tmK, tmV, tmdO, tmDQ, tmDK, tmDV, lse, delta, kv_len, slopes, sh);
+#else
   if (!set) {
     VG_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     set = true;
   }
-  AttnTcShape sh{B, H, Tq, Tk, q_offset, scale, g_attn_trace};
   dim3 grid((unsigned)((Tk + TK - 1) / TK) * (unsigned)H * (unsigned)B);
   attn_tc_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, tmDK, tmDV, lse, delta, kv_len,
                                                           slopes, sh);
+#endif
   VG_LAUNCH_CHECK("vg_attn_bwd(tcgen05)");
   const int C = H * HD;
   const int64_t n = (int64_t)B * Tq * (C / 8);
