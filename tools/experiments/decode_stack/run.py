@@ -9,13 +9,14 @@ import sys
 import torch
 
 here = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, here)
 lib = C.CDLL(os.path.join(here, "libds.so"))
-DM, NH, HD, FF, OWNERS, MAXL = 1024, 16, 64, 4096, 128, 16
-NA, NC, NF, XS, D2S = 24, 8, 32, 1032, 36
+from common import (D2S, DM, EPS, FF, HD, MAXL, NA, NC, NF, NH, OWNERS, SCALE, XS, alibi_slopes, bf, make_layers, pack_rows,  # noqa: E402,F401
+                    pack_w2, reference)
+
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 PROMPT = int(sys.argv[2]) if len(sys.argv) > 2 else 180
 dev = torch.device("cuda")
-bf = torch.bfloat16
 
 
 class Layer(C.Structure):
@@ -29,58 +30,10 @@ class Params(C.Structure):
                 ("out", C.c_void_p)]
 
 
-def pack_rows(w, rows_per_owner):
-    """[N, 1024] bf16 → [OWNERS][rows_per_owner][XS] (zero padded): the shared-memory image of each owner's slab."""
-    n = w.shape[0]
-    assert n == OWNERS * rows_per_owner
-    out = torch.zeros(OWNERS, rows_per_owner, XS, dtype=bf, device=dev)
-    out[..., :DM] = w.view(OWNERS, rows_per_owner, DM)
-    return out.contiguous()
-
-
-def pack_w2(w2):
-    """W2 [1024, 4096] → [OWNERS][1024 n][D2S]: owner c holds the k-slice [32c, 32c + 32) of every output row."""
-    out = torch.zeros(OWNERS, DM, D2S, dtype=bf, device=dev)
-    out[..., :NF] = w2.view(DM, OWNERS, NF).permute(1, 0, 2)
-    return out.contiguous()
-
-
-def alibi_slopes(h):
-    return torch.tensor([2.0 ** (-(i + 1) / 2) for i in range(h)], dtype=torch.float32, device=dev)   # alibi.py: 2^(-(h+1)/2)
-
-
-torch.manual_seed(0)
+layers = make_layers(L, dev)
+slopes = alibi_slopes(NH, dev)
+eps, scale = EPS, SCALE
 g = lambda *s, sc=1.0: (torch.randn(*s, device=dev) * sc)          # noqa: E731
-layers = []
-for _ in range(L):
-    layers.append(dict(w_in=g(3 * DM, DM, sc=DM ** -0.5).to(bf), w_out=g(DM, DM, sc=DM ** -0.5).to(bf),
-                       w1=g(FF, DM, sc=DM ** -0.5).to(bf), w2=g(DM, FF, sc=FF ** -0.5).to(bf),
-                       n1=1 + 0.1 * g(DM), n3=1 + 0.1 * g(DM), b1=0.1 * g(FF), b2=0.1 * g(DM)))
-slopes = alibi_slopes(NH)
-eps, scale = 1e-6, 1.0 / math.sqrt(HD)
-
-
-def rms(x, w):
-    return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * w
-
-
-def reference(x, kcs, vcs, pos):
-    """fp32 stack on [B, 1024]; kcs / vcs: per-layer fp32 caches [B, H, Tmax, 64] holding `pos` past rows."""
-    B = x.shape[0]
-    for ly, kc, vc in zip(layers, kcs, vcs):
-        qkv = rms(x, ly["n1"]) @ ly["w_in"].float().t()
-        q, k, v = (t.view(B, NH, HD) for t in qkv.split(DM, -1))
-        kc[:, :, pos] = k.to(bf).float()
-        vc[:, :, pos] = v.to(bf).float()
-        s = torch.einsum("bhd,bhtd->bht", q, kc[:, :, :pos + 1]) * scale
-        s = s - slopes.view(1, NH, 1) * (pos - torch.arange(pos + 1, device=dev)).view(1, 1, -1)
-        o = torch.einsum("bht,bhtd->bhd", torch.softmax(s, -1), vc[:, :, :pos + 1]).reshape(B, DM)
-        x = x + o.to(bf).float() @ ly["w_out"].float().t()
-        hdn = torch.nn.functional.gelu(rms(x, ly["n3"]) @ ly["w1"].float().t() + ly["b1"])
-        x = x + hdn @ ly["w2"].float().t() + ly["b2"]
-    return x
-
-
 packed = [dict(A=pack_rows(ly["w_in"], NA), Cc=pack_rows(ly["w_out"], NC), D1=pack_rows(ly["w1"], NF), D2=pack_w2(ly["w2"]))
           for ly in layers]
 assert packed[0]["A"][0].numel() * 2 == lib.ds_slab_bytes(0) and packed[0]["D2"][0].numel() * 2 == lib.ds_slab_bytes(3)
@@ -90,7 +43,7 @@ for B in (1, 4, 8):
     x0 = g(B, DM)
     kc = [g(B, NH, Tmax, HD, sc=0.5).to(bf) for _ in range(L)]
     vc = [g(B, NH, Tmax, HD, sc=0.5).to(bf) for _ in range(L)]
-    want = reference(x0.clone(), [k.float() for k in kc], [v.float() for v in vc], PROMPT)
+    want = reference(layers, slopes, x0.clone(), [k.float() for k in kc], [v.float() for v in vc], PROMPT)
     hres = [x0.clone(), torch.zeros_like(x0)]
     facc = [torch.zeros_like(x0), torch.zeros_like(x0)]
     qbuf, abuf = torch.zeros_like(x0), torch.zeros(B, DM, dtype=bf, device=dev)
