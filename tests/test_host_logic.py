@@ -162,3 +162,30 @@ def test_lr_schedule_closed_form():
     assert cosine_lr(1000000, 5e-4, 5e-5, 30000, 1000000) == pytest.approx(5e-5)
     mid = cosine_lr(30000 + 485000, 5e-4, 5e-5, 30000, 1000000)
     assert mid == pytest.approx((5e-4 + 5e-5) / 2)
+
+
+def test_seeded_init_is_bit_identical_to_reference():
+    """under torch.manual_seed(0) this repo's LVTR + init_weights produces, tensor for tensor and in
+    the same state-dict order, the bytes of the REAL reference's LVTR + BaseTrainer.init_weights
+    (training_lib/trainer.py:113-125) at the full configuration.  The reference side is the committed digest
+    tests/golden/init_digest.json (made by tests/golden/make_init_digest.py in the build container)."""
+    import hashlib
+    import json
+    from vae_gslm_b200.models.speech.lvtr import LVTR
+    from vae_gslm_b200.training_lib.trainer import init_weights
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = json.load(open(os.path.join(root, "tests", "golden", "init_digest.json")))
+    hp = Hparams.from_yamlfile(os.path.join(root, "vae_gslm_b200", "configs", "train", "speech", "vae-gslm.yaml"))
+    torch.manual_seed(ref["seed"])
+    model = LVTR(hp.model, input_dim=80)
+    model.apply(init_weights)
+    assert sum(p.numel() for p in model.parameters()) == ref["n_params"] == 226957564
+    sd = model.state_dict()
+    assert list(sd.keys()) == [e["name"] for e in ref["entries"]]
+    bad = []
+    for e in ref["entries"]:
+        t = sd[e["name"]].detach().cpu().contiguous()
+        if list(t.shape) != e["shape"] or str(t.dtype).replace("torch.", "") != e["dtype"] \
+                or hashlib.sha256(t.numpy().tobytes()).hexdigest() != e["sha256"]:
+            bad.append(e["name"])
+    assert not bad, bad[:10]

@@ -353,10 +353,6 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 64) AT_MARK(4);
 }
 
-#if defined(VG_ATTN_FWD_SPLIT) && VG_ATTN_FWD_SPLIT == 2
-#include "attn_tc_fwd_split.cuh"
-#endif
-
 // =========================================================================================== backward
 constexpr int BWD_EW = 16;                  // elementwise warps: four per TMEM lane quadrant, 32 of the 128 key columns each
 constexpr int BWD_THREADS = 64 + 32 * BWD_EW;      // + TMA producer warp + MMA issuer warp
@@ -689,7 +685,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 64) AT_MARK(4);
 }
 
-#if defined(VG_ATTN_BWD_PERSIST) && VG_ATTN_BWD_PERSIST
+// Persistent backward (one CTA per SM walking a heavy-first item list, next item's K/V prefetched under the dK/dV
+// epilogue): measured on B200 112 vs 121 us at B=8,T=1000 and 65 vs 73 us at T=640 (profiles/r02_variants.md); default.
+// -DVG_ATTN_BWD_PERSIST=0 selects the one-CTA-per-key-tile kernel above.
+#ifndef VG_ATTN_BWD_PERSIST
+#define VG_ATTN_BWD_PERSIST 1
+#endif
+#if VG_ATTN_BWD_PERSIST
 #include "attn_tc_bwd_persist.cuh"
 #endif
 
@@ -753,19 +755,11 @@ int attn_tc_fwd_launch(const void* q, const void* k, const void* v, int64_t ld_q
   AttnTcShape sh{B, H, Tq, Tk, q_offset, scale, g_attn_trace};
   dim3 grid((unsigned)((Tq + TQ - 1) / TQ) * (unsigned)H * (unsigned)B);
   static bool set = false;
-#if defined(VG_ATTN_FWD_SPLIT) && VG_ATTN_FWD_SPLIT == 2
-  if (!set) {
-    VG_CUDA(cudaFuncSetAttribute(attn_tc_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWDS_SMEM));
-    set = true;
-  }
-  attn_tc_fwd_split_kernel<<<grid, FWDS_THREADS, FWDS_SMEM, st>>>(tmQ, tmK, tmV, tmO, lse, kv_len, slopes, sh);
-#else
   if (!set) {
     VG_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     set = true;
   }
   attn_tc_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmK, tmV, tmO, lse, kv_len, slopes, sh);
-#endif
   VG_LAUNCH_CHECK("vg_attn_fwd(tcgen05)");
   return 0;
 }
@@ -800,7 +794,7 @@ int attn_tc_bwd_launch(const void* dout, int64_t ld_dout, const void* q, const v
   if ((rc = make_tmap_bf16_3d(&tmDV, dv, (int64_t)H * HD, Tk, B, ld_dkv, (int64_t)Tk * ld_dkv, HD, 32))) return rc;
   AttnTcShape sh{B, H, Tq, Tk, q_offset, scale, g_attn_trace};
   static bool set = false;
-#if defined(VG_ATTN_BWD_PERSIST) && VG_ATTN_BWD_PERSIST
+#if VG_ATTN_BWD_PERSIST
   static int sms = 0;
   if (!set) {
     int dev = 0;

@@ -2,7 +2,7 @@
 // per-operand-layout translation units gemm_tc_{kk,kmn,mnk,mnmn}.cu so that they compile in parallel.
 #pragma once
 #ifndef VG_GEMM_UNIFORM_ISSUE
-#define VG_GEMM_UNIFORM_ISSUE 0
+#define VG_GEMM_UNIFORM_ISSUE 1
 #endif
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
@@ -397,11 +397,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_units = num_m * num_n * epi.splits;
   const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
 
-  // VG_GEMM_UNIFORM_ISSUE (compile-time, default 0): the producer / MMA-issuer warps walk their loops as whole warps and
+  // VG_GEMM_UNIFORM_ISSUE (compile-time, default 1): the producer / MMA-issuer warps walk their loops as whole warps and
   // one elect.sync-elected lane issues.  Inside a `lane == 0` branch the compiler wraps every TMA / tcgen05.mma in a
   // per-thread ELECT / R2UR / BRA.U.ANY loop (~80 cycles per instruction: measured in the attention kernels, where the
   // same change made the MMAs issue back to back — profiles/r01_attention_v2.md); with 128-wide tiles (64 tensor cycles
-  // per MMA) that is issue-bound.  Prepared, not yet measured on the GEMM: the default build is unchanged.
+  // per MMA) that is issue-bound.  Measured on B200 (profiles/r02_variants.md): fwd qkv 0.88 -> 0.99x cuBLAS, fwd ffn1
+  // 0.99 -> 1.07x, dgrad ffn2 1.04 -> 1.13x, nothing slower; -DVG_GEMM_UNIFORM_ISSUE=0 restores the lane-0 branches.
   constexpr bool kUniformIssue = VG_GEMM_UNIFORM_ISSUE != 0;
   if (warp == 0 && (kUniformIssue || lane == 0)) {
     // ===================== TMA producer (every CTA loads its own A rows and its own slice of B) =====================
