@@ -341,6 +341,62 @@ int vg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vg_stream_t stre
  * big matrices are overwritten by their first weight-gradient GEMM of the step (beta = 0) instead. */
 int vg_zero_segments(float* base, const int64_t* seg_off, const int64_t* seg_len, int n_seg, vg_stream_t stream);
 
+/* ---- persistent cached-generation step: the transformer part of LVTR.step (models/speech/lvtr.py:253-279 →
+ * modules/transformer/layers.py:134-195 with past_kv, modules/attention/attention.py:52-85, modules/norm.py:28-32,
+ * lvtr.py:171,172,194,195) as ONE cooperative launch — stack-input linear, L x [RMSNorm1+QKV | cached attention + KV append |
+ * out-proj+residual | RMSNorm3+FFN1 | GELU+FFN2+residual], final RMSNorm, q_spliter|token_spliter, prior/FiLM head, logits.
+ * The step is a list of NP phases separated by device-wide barriers.  In a GEMM phase every CTA runs at most one unit of
+ * the host-built task table `tasks[grid][NP]` (vae_gslm_b200/decode_step.py builds it): `R` (multiple of 8, <= 128) output
+ * features x `nkb` 64-wide k-blocks of one linear layer as a swap-AB tcgen05 GEMM whose weight slab comes from the CTA's
+ * own packed byte stream (`wstream + wstream_off[cta]`: per unit, per k-block, R/8 SWIZZLE_128B atoms of 8 rows x 64 bf16,
+ * in consumption order) and whose X operand the CTA forms from `x` (x_kind 0: bf16 rows; 1: f32 rows * vec[k], optionally
+ * accumulating the row sum-of-squares into ss_out; 2: act(f32 rows * rsqrt(ss_in[b]*inv_k + eps) + vec[k])).  The
+ * accumulator rows are reduced (red.global.add.f32) or stored into acc[b*ldacc + n0 + r] (+ bias_out[n0 + r]).
+ * phase_kind[p] < 0: GEMM phase; >= 0: attention phase of that layer over the head-major cache
+ * [L][2][B][H][Tmax][64] bf16 (reads the QKV sums of the phase before, appends k/v at *pos_dev).
+ * aux jobs: 1 = clear aux_i1 float4 at float4 index aux_i0 of aux_ptr0; 2 = write bf16 transformer_latent groups.
+ * State carried between launches (caller-allocated, zero-initialised once): bar_flags [grid] u32, epoch u32, tickets.   */
+typedef struct {
+  const void* x;            /* X source rows */
+  float* acc;               /* accumulator [B, ldacc] f32 */
+  const float* vec;         /* per-k scale (x_kind 1) or bias (x_kind 2) */
+  const float* ss_in;       /* [B] row sum-of-squares for x_kind 2 (nullable: rstd = 1) */
+  float* ss_out;            /* [B] accumulated by this unit (x_kind 1; nullable) */
+  const float* bias_out;    /* added to this unit's accumulator rows (nullable) */
+  void* aux_ptr0; void* aux_ptr1; void* aux_ptr2; void* aux_ptr3;
+  int32_t ldx, ldacc;
+  int32_t k0, nkb;
+  int32_t n0, rows;         /* first feature, number of valid features (<= R) */
+  int32_t R;                /* padded rows of the packed slab; 0 = no GEMM unit in this phase */
+  int32_t x_kind, act, store;
+  float inv_k, eps;
+  int32_t aux_kind, aux_i0, aux_i1, aux_i2;
+} vg_decode_step_task;
+
+typedef struct {
+  const vg_decode_step_task* tasks;      /* [grid][NP] */
+  const int32_t* phase_kind;             /* [NP] */
+  const uint8_t* wstream; const int64_t* wstream_off;   /* packed weights, per-CTA byte offsets [grid] */
+  /* attention phases */
+  const float* qkv_acc;                  /* [B, 3*H*64] f32 sums of the QKV phase */
+  const float* ss_base;                  /* row sum-of-squares arrays: layer l's RMSNorm1 at ss_base + 2*l*B */
+  void* cache;                           /* bf16 [L][2][B][H][Tmax][64] */
+  int64_t cache_layer_stride, cache_kv_stride;          /* in elements */
+  void* attn_out;                        /* bf16 [B, H*64] */
+  const float* slopes;                   /* [H] ALiBi slopes (nullable) */
+  float* attn_partial;                   /* [B*H*nsplit*(64+2)] f32 (nsplit > 1) */
+  int32_t* tickets;                      /* [B*H], zero on entry and left zero */
+  int32_t* pos_dev;                      /* number of cached positions; advanced by the kernel when advance_pos */
+  uint32_t* bar_flags; uint32_t* epoch;  /* barrier state, persistent across launches */
+  unsigned long long* debug;             /* nullable: [8] words written before a time-out trap */
+  long long* trace;                      /* nullable: [grid][NP][8] clock64 stamps (barrier entry / exit, unit stages) */
+  float inv_d, eps, scale;               /* 1/d_model, RMSNorm eps, softmax scale */
+  int32_t NP, grid, B, Bp, H, Tmax, nsplit, barrier_mode, advance_pos;
+} vg_decode_step_args;
+size_t vg_decode_step_task_bytes(void);
+size_t vg_decode_step_smem_bytes(int32_t n_phases);
+int    vg_decode_step(const vg_decode_step_args* a, vg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

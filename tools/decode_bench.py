@@ -22,7 +22,15 @@ model = model.to(dev).set_compute_dtype(torch.bfloat16).eval()
 batches = tuple(int(a) for a in sys.argv[1:] if a.isdigit()) or (1, 8, 64, 256)
 if "--force-engine" in sys.argv:
     model.decode_engine_max_batch = 256
-for engine in ((True, False) if "--both" in sys.argv else (True,)):
-    model.use_decode_engine = engine
-    out = bench.decode_bench(model, dev, bench.measured_peaks(), batches=batches)
-    print("engine" if engine else "layerwise", json.dumps(out), flush=True)
+kinds = [a.split("=")[1] for a in sys.argv if a.startswith("--kind=")] or ["step"]
+if "--both" in sys.argv:
+    kinds = ["step", "linear", "layerwise"]
+gen = int(([a.split("=")[1] for a in sys.argv if a.startswith("--gen=")] or ["500"])[0])
+for kind in kinds:
+    model.use_decode_engine = kind != "layerwise"
+    model.decode_engine_kind = kind
+    if kind == "linear" and "--force-engine" not in sys.argv:
+        model.decode_engine_max_batch = 96
+    out = bench.decode_bench(model, dev, bench.measured_peaks(), batches=batches, gen=gen, ddim=False)
+    for k, v in out.items():
+        print(kind, k, json.dumps(v), flush=True)

@@ -161,6 +161,9 @@ _SIGNATURES = {
     "vg_adamw_step": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _p, _p]),
     "vg_zero_segments": (C.c_int, [_p, _p, _p, C.c_int, _p]),
     "vg_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
+    "vg_decode_step_task_bytes": (_sz, []),
+    "vg_decode_step_smem_bytes": (_sz, [_i32]),
+    "vg_decode_step": (C.c_int, [_p, _p]),
 }
 
 _lib: Optional[C.CDLL] = None

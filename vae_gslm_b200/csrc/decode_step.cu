@@ -1,0 +1,634 @@
+// decode_step.cu — ONE persistent kernel for the transformer part of a cached generation step (LVTR.step,
+// models/speech/lvtr.py:253-279 → modules/transformer/layers.py:134-195 with past_kv, modules/attention/attention.py:52-85,
+// modules/norm.py:28-32): stack-input linear, 16 x [RMSNorm1 + QKV, cached attention (+ KV append), out-proj + residual,
+// RMSNorm3 + FFN1 + GELU, FFN2 + residual], final RMSNorm, q_spliter | token_spliter (+ReLU), prior/FiLM head and logit head.
+//
+// Why one kernel: the step is HBM-bound (408.7 MB of bf16 weights + the KV cache) but the 92-kernel engine of
+// round 1 (decode.py) was bound by kernel boundaries (~5 us each, 0.47 ms at batch 1 against 63 us of weight streaming).
+// Here one CTA per SM stays resident for the whole step:
+//   * WEIGHTS never wait for activations: the host packs, per CTA, the exact byte stream of weight slabs that CTA will
+//     consume (in order, already in the tcgen05 SWIZZLE_128B K-major shared-memory layout), and a producer warp copies it
+//     with 1-D bulk TMA (cp.async.bulk → UBLKCP) through an 8 x 16 KB ring, running ahead across phase boundaries — the HBM
+//     stream does not stop at a barrier;
+//   * the step is a list of PHASES separated by device-wide barriers; in a GEMM phase every CTA executes at most one UNIT
+//     (R <= 128 output features x a k-range of one linear layer) described by a host-built task table — the decomposition
+//     per batch size (small batch: few features x full K per CTA; large batch: 128 features x a k-slice) is host policy,
+//     the kernel is an interpreter;
+//   * a unit is a swap-AB tcgen05 GEMM: D[128 features x Bp batch columns] (TMEM, fp32) += W_slab[128 x 64] · Xᵀ[64 x Bp]
+//     per 64-wide k-block, weights as the M operand so that batch 1..256 is one code path (N = 16..256);
+//   * the X operand is formed by the CONSUMER: worker warps read the producer phase's fp32 accumulators (L2), apply what the
+//     reference applies between the two linears (RMSNorm scale / 1/rms, bias + GELU / ReLU), round to bf16 and store the
+//     swizzled K-major tile — so split-K partial sums (red.global.add.f32 from the epilogue) need no finishing pass;
+//   * the residual stream is an fp32 [B, d] buffer that out-proj and FFN2 units reduce into directly;
+//   * attention phases walk (sequence, head, kv-split) items over the head-major cache, 8 lanes per key row, online softmax
+//     per 8-lane group, in-kernel merge of split partials by the last arriver.
+// Every spin (mbarrier or global) is bounded: on time-out the kernel records where it was and traps instead of hanging.
+#include <math_constants.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace vg {
+using namespace sm100;
+
+constexpr int DS_THREADS = 256;            // warp 0: weight producer, warp 1: MMA issuer, warps 2..7: workers (4..7: epilogue)
+constexpr int DS_WORKERS = 192;
+constexpr int DS_STAGE = 16384;            // weight ring stage
+constexpr int DS_NSTAGES = 8;
+constexpr int DS_XSLOT = 32768;            // X operand slot (two of them)
+constexpr int DS_HD = 64;                  // head dim
+constexpr int DS_GROUPS = (DS_WORKERS / 32) * 4;    // 24 key groups of 8 lanes
+constexpr int DS_KUNROLL = 4;
+constexpr long long DS_TIMEOUT = 4000000000LL;      // ~2 s of SM clocks
+
+typedef vg_decode_step_task DsTask;
+typedef vg_decode_step_args DsArgs;
+
+struct DsShared {
+  uint64_t full[DS_NSTAGES], empty[DS_NSTAGES], xfull[2], xempty[2], accfull;
+  uint32_t tmem_base;
+  int last;
+  float m[DS_GROUPS], l[DS_GROUPS];
+  float o[DS_GROUPS][DS_HD];
+  float ss[256];
+  int phase_kind[128];
+};
+
+__device__ __forceinline__ void ds_die(const DsArgs& a, int code, int phase) {
+  if (a.debug) {
+    a.debug[0] = 0xDEAD0000ull | (unsigned)code;
+    a.debug[1] = ((unsigned long long)blockIdx.x << 32) | (unsigned)phase;
+    a.debug[2] = threadIdx.x;
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void ds_mbar_wait(uint64_t* bar, uint32_t parity, const DsArgs& a, int code, int phase) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > DS_TIMEOUT) ds_die(a, code, phase);
+}
+__device__ __forceinline__ void ds_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ unsigned ds_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ds_ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ds_bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void ds_red_add(float* p, float v) {
+  asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ds_pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ds_round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// ---- device-wide barrier (warps 1..7; the producer warp never stops).  mode 0: every CTA publishes the epoch in its own
+// flag word and one warp polls all flags (no atomics, no same-address serialisation); mode 1: one monotonic counter.
+__device__ __forceinline__ void ds_grid_barrier(const DsArgs& a, unsigned epoch, int phase) {
+  ds_named_bar(1, DS_THREADS - 32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (a.trace && threadIdx.x == 32) a.trace[((size_t)blockIdx.x * a.NP + phase) * 8] = clock64();
+  if (warp == 1) {
+    const unsigned G = gridDim.x;
+    if (a.barrier_mode == 0) {
+      if (lane == 0) {
+        __threadfence();
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.bar_flags + blockIdx.x), "r"(epoch) : "memory");
+      }
+      const long long t0 = clock64();
+      for (;;) {
+        bool ok = true;
+        for (unsigned i = lane; i < G; i += 32) ok = ok & ((int)(ds_ld_relaxed(a.bar_flags + i) - epoch) >= 0);
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 100, phase);
+      }
+      __threadfence();
+    } else if (a.barrier_mode == 1) {
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(a.bar_flags, 1u);
+        const unsigned target = epoch * G;
+        const long long t0 = clock64();
+        while ((int)(ds_ld_acquire(a.bar_flags) - target) < 0)
+          if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 101, phase);
+        __threadfence();
+      }
+    } else {
+      // mode 2: flags gathered by CTA 0 (148 loads per poll round instead of 148 x 148 on one L2 slice), which publishes
+      // one "go" word (a different cache line) that everybody else polls
+      unsigned* go = a.bar_flags + ((G + 63u) & ~31u);
+      if (lane == 0) {
+        __threadfence();
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.bar_flags + blockIdx.x), "r"(epoch) : "memory");
+      }
+      const long long t0 = clock64();
+      if (blockIdx.x == 0) {
+        for (;;) {
+          bool ok = true;
+          for (unsigned i = lane; i < G; i += 32) ok = ok & ((int)(ds_ld_relaxed(a.bar_flags + i) - epoch) >= 0);
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 102, phase);
+        }
+        __threadfence();
+        if (lane == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(epoch) : "memory");
+      } else {
+        if (lane == 0) {
+          while ((int)(ds_ld_relaxed(go) - epoch) < 0)
+            if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 103, phase);
+        }
+        __syncwarp();
+        __threadfence();
+      }
+    }
+  }
+  if (a.trace && threadIdx.x == 32) a.trace[((size_t)blockIdx.x * a.NP + phase) * 8 + 1] = clock64();
+  ds_named_bar(1, DS_THREADS - 32);
+}
+
+#define DS_TRACE(slot, thread) \
+  do { if (a.trace && threadIdx.x == (thread)) a.trace[((size_t)blockIdx.x * a.NP + p) * 8 + (slot)] = clock64(); } while (0)
+
+// ---- X operand: worker warps form the bf16, SWIZZLE_128B K-major [Bp x 64] tiles of this unit's k-range.
+//   kind 0: x bf16 [B, ldx] as is          kind 1: x f32 * vec[k]   (RMSNorm scale; 1/rms is applied by the consumer of the sums)
+//   kind 2: act(x f32 * rstd[b] + vec[k])  (rstd from the row sum-of-squares the kind-1 phase accumulated)
+__device__ __forceinline__ void ds_transform(const DsArgs& a, const DsTask& t, DsShared& sh, uint8_t* xs, uint32_t& xcount,
+                                             int phase) {
+  const int p = phase;
+  const int wt = threadIdx.x - 64;
+  const int lane = threadIdx.x & 31;
+  const int B = a.B, Bp = a.Bp;
+  const int cap = DS_XSLOT / (Bp * 128);
+  const int xkb = t.nkb < cap ? t.nkb : cap;
+  const int nchunks = t.nkb / xkb;
+  const int per_b = xkb * 8;
+  const int items = B * per_b;
+  const int items_pad = (items + 31) & ~31;
+  const bool want_ss = t.ss_out != nullptr;
+  for (int c = 0; c < nchunks; ++c) {
+    const int slot = xcount & 1;
+    const uint32_t use = xcount >> 1;
+    if (use > 0) ds_mbar_wait(&sh.xempty[slot], (use - 1) & 1, a, 10, phase);
+    uint8_t* dst = xs + slot * DS_XSLOT;
+    for (int item = wt; item < items_pad; item += DS_WORKERS) {
+      float ssq = 0.f;
+      int b = 0;
+      if (item < items) {
+        b = item / per_b;
+        const int rem = item - b * per_b;
+        const int j = rem >> 3, g = rem & 7;
+        const int k = t.k0 + (c * xkb + j) * 64 + g * 8;
+        uint4 packed;
+        if (t.x_kind == 0) {
+          packed = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t.x) + (size_t)b * t.ldx + k));
+        } else {
+          const float* src = reinterpret_cast<const float*>(t.x) + (size_t)b * t.ldx + k;
+          const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src));
+          const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src) + 1);
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(t.vec + k));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(t.vec + k) + 1);
+          float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          if (t.x_kind == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ssq = fmaf(v[i], v[i], ssq); v[i] *= s[i]; }
+          } else {
+            const float rstd = t.ss_in ? rsqrtf(__ldcg(t.ss_in + b) * t.inv_k + t.eps) : 1.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float y = fmaf(v[i], rstd, s[i]);
+              v[i] = t.act == VG_ACT_GELU ? gelu_fast(y) : (t.act == VG_ACT_RELU ? fmaxf(y, 0.f) : y);
+            }
+          }
+          packed.x = ds_pack_bf16(v[0], v[1]); packed.y = ds_pack_bf16(v[2], v[3]);
+          packed.z = ds_pack_bf16(v[4], v[5]); packed.w = ds_pack_bf16(v[6], v[7]);
+        }
+        *reinterpret_cast<uint4*>(dst + j * (Bp * 128) + (b >> 3) * 1024 + (b & 7) * 128 + ((g ^ (b & 7)) << 4)) = packed;
+      }
+      if (want_ss) {
+        // lanes of one batch row are contiguous: per_b (a power of two >= 8) lanes per row when per_b < 32, else whole warps
+        const int seg = per_b < 32 ? per_b : 32;
+        for (int o = 1; o < seg; o <<= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+        if ((lane & (seg - 1)) == 0 && item < items) atomicAdd(&sh.ss[b], ssq);
+      }
+    }
+    fence_proxy_async();
+    mbar_arrive(&sh.xfull[slot]);
+    if (c == 0) DS_TRACE(7, 64);
+    ++xcount;
+  }
+  if (want_ss) {
+    ds_named_bar(2, DS_WORKERS);
+    for (int b = wt; b < B; b += DS_WORKERS) {
+      ds_red_add(t.ss_out + b, sh.ss[b]);
+      sh.ss[b] = 0.f;
+    }
+  }
+}
+
+// ---- auxiliary jobs of a phase (warps 2..3, off the critical path): clear accumulators for a later phase, write H
+__device__ __forceinline__ void ds_aux(const DsTask& t) {
+  const int at = threadIdx.x - 64;              // 0..63
+  if (t.aux_kind == 1) {                        // zero aux_i1 float4s starting at float4 index aux_i0 of aux_ptr0
+    float4* p = reinterpret_cast<float4*>(t.aux_ptr0) + t.aux_i0;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = at; i < t.aux_i1; i += 64) p[i] = z;
+  } else if (t.aux_kind == 2) {
+    // transformer_latent rows: H[b,k] = bf16(h[b,k] * scale[k] * rstd[b]); groups of 8 elements aux_i0 .. aux_i0+aux_i1
+    const float* h = reinterpret_cast<const float*>(t.aux_ptr0);
+    const float* scale = reinterpret_cast<const float*>(t.aux_ptr1);
+    const float* ss = reinterpret_cast<const float*>(t.aux_ptr2);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(t.aux_ptr3);
+    const int d = t.aux_i2;                     // model dim
+    for (int i = at; i < t.aux_i1; i += 64) {
+      const int e = (t.aux_i0 + i) * 8;
+      const int b = e / d, k = e - b * d;
+      const float rstd = rsqrtf(__ldcg(ss + b) * t.inv_k + t.eps);
+      const float4 v0 = __ldcg(reinterpret_cast<const float4*>(h + e));
+      const float4 v1 = __ldcg(reinterpret_cast<const float4*>(h + e) + 1);
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + k));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + k) + 1);
+      uint4 q;
+      q.x = ds_pack_bf16(v0.x * s0.x * rstd, v0.y * s0.y * rstd);
+      q.y = ds_pack_bf16(v0.z * s0.z * rstd, v0.w * s0.w * rstd);
+      q.z = ds_pack_bf16(v1.x * s1.x * rstd, v1.y * s1.y * rstd);
+      q.w = ds_pack_bf16(v1.z * s1.z * rstd, v1.w * s1.w * rstd);
+      *reinterpret_cast<uint4*>(out + e) = q;
+    }
+  }
+}
+
+// ---- attention phase: items (b, h, split) over the head-major KV cache; the new token's k / v come from the QKV sums
+__device__ __forceinline__ void ds_attention(const DsArgs& a, DsShared& sh, int layer, int pos, int phase) {
+  const int wt = threadIdx.x - 64;
+  const int lane = threadIdx.x & 31;
+  const int grp = (wt >> 5) * 4 + (lane >> 3);
+  const int sub = lane & 7;
+  const int H = a.H, HD = a.H * DS_HD;
+  const int nsplit = a.nsplit;
+  const int n_items = a.B * H * nsplit;
+  const int nkeys = pos + 1;
+  const int chunk = (nkeys + nsplit - 1) / nsplit;
+  const float* ss = a.ss_base + (size_t)(2 * layer) * a.B;
+  constexpr float LOG2E = 1.4426950408889634f;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int split = item % nsplit;
+    const int bh = item / nsplit;
+    const int h = bh % H, b = bh / H;
+    const float rstd = rsqrtf(__ldcg(ss + b) * a.inv_d + a.eps);
+    const float* row = a.qkv_acc + (size_t)b * 3 * HD + h * DS_HD + sub * 8;
+    float q[8];
+    {
+      const float4 q0 = __ldcg(reinterpret_cast<const float4*>(row));
+      const float4 q1 = __ldcg(reinterpret_cast<const float4*>(row) + 1);
+      const float f = rstd * a.scale * LOG2E;
+      q[0] = q0.x * f; q[1] = q0.y * f; q[2] = q0.z * f; q[3] = q0.w * f;
+      q[4] = q1.x * f; q[5] = q1.y * f; q[6] = q1.z * f; q[7] = q1.w * f;
+    }
+    const float slope = (a.slopes ? a.slopes[h] : 0.f) * LOG2E;
+    __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(a.cache) + (size_t)layer * a.cache_layer_stride + ((size_t)b * H + h) * (size_t)a.Tmax * DS_HD;
+    __nv_bfloat16* vc = kc + a.cache_kv_stride;
+    const int j_begin = split * chunk;
+    const int j_end = min(nkeys, j_begin + chunk);
+    float m = -CUDART_INF_F, l = 0.f, acc[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+    for (int base = j_begin; base < j_end; base += DS_GROUPS * DS_KUNROLL) {
+      uint4 kraw[DS_KUNROLL], vraw[DS_KUNROLL];
+#pragma unroll
+      for (int u = 0; u < DS_KUNROLL; ++u) {
+        const int j = base + u * DS_GROUPS + grp;
+        if (j < j_end && j != pos) {
+          kraw[u] = __ldcs(reinterpret_cast<const uint4*>(kc + (size_t)j * DS_HD + sub * 8));
+          vraw[u] = __ldcs(reinterpret_cast<const uint4*>(vc + (size_t)j * DS_HD + sub * 8));
+        } else if (j == pos && j < j_end) {
+          // the new token: k, v = bf16(sum * rstd) of this step's QKV accumulators; appended to the cache here
+          const float4 k0 = __ldcg(reinterpret_cast<const float4*>(row + HD));
+          const float4 k1 = __ldcg(reinterpret_cast<const float4*>(row + HD) + 1);
+          const float4 v0 = __ldcg(reinterpret_cast<const float4*>(row + 2 * HD));
+          const float4 v1 = __ldcg(reinterpret_cast<const float4*>(row + 2 * HD) + 1);
+          kraw[u].x = ds_pack_bf16(k0.x * rstd, k0.y * rstd); kraw[u].y = ds_pack_bf16(k0.z * rstd, k0.w * rstd);
+          kraw[u].z = ds_pack_bf16(k1.x * rstd, k1.y * rstd); kraw[u].w = ds_pack_bf16(k1.z * rstd, k1.w * rstd);
+          vraw[u].x = ds_pack_bf16(v0.x * rstd, v0.y * rstd); vraw[u].y = ds_pack_bf16(v0.z * rstd, v0.w * rstd);
+          vraw[u].z = ds_pack_bf16(v1.x * rstd, v1.y * rstd); vraw[u].w = ds_pack_bf16(v1.z * rstd, v1.w * rstd);
+          *reinterpret_cast<uint4*>(kc + (size_t)pos * DS_HD + sub * 8) = kraw[u];
+          *reinterpret_cast<uint4*>(vc + (size_t)pos * DS_HD + sub * 8) = vraw[u];
+        } else {
+          kraw[u] = make_uint4(0, 0, 0, 0);
+          vraw[u] = make_uint4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < DS_KUNROLL; ++u) {
+        const int j = base + u * DS_GROUPS + grp;
+        const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kraw[u]);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(k2[i]);
+          s = fmaf(q[2 * i], f.x, s);
+          s = fmaf(q[2 * i + 1], f.y, s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (j < j_end) {
+          s -= slope * (float)(pos - j);
+          const float mnew = fmaxf(m, s);
+          const float corr = ex2_approx(m - mnew);           // m = -inf on the first key → 0
+          const float pr = ex2_approx(s - mnew);
+          l = l * corr + pr;
+          const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vraw[u]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(v2[i]);
+            acc[2 * i] = fmaf(pr, f.x, acc[2 * i] * corr);
+            acc[2 * i + 1] = fmaf(pr, f.y, acc[2 * i + 1] * corr);
+          }
+          m = mnew;
+        }
+      }
+    }
+    if (sub == 0) { sh.m[grp] = m; sh.l[grp] = l; }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) sh.o[grp][sub * 8 + d] = acc[d];
+    ds_named_bar(2, DS_WORKERS);
+    float M = -CUDART_INF_F, Lsum = 0.f, O = 0.f;
+    if (wt < DS_HD) {
+#pragma unroll
+      for (int g = 0; g < DS_GROUPS; ++g) M = fmaxf(M, sh.m[g]);
+      if (M != -CUDART_INF_F) {
+#pragma unroll
+        for (int g = 0; g < DS_GROUPS; ++g) {
+          const float w = (sh.m[g] == -CUDART_INF_F) ? 0.f : ex2_approx(sh.m[g] - M);
+          Lsum = fmaf(sh.l[g], w, Lsum);
+          O = fmaf(sh.o[g][wt], w, O);
+        }
+      }
+      if (nsplit == 1) {
+        reinterpret_cast<__nv_bfloat16*>(a.attn_out)[(size_t)b * HD + h * DS_HD + wt] = __float2bfloat16_rn(Lsum > 0.f ? O / Lsum : 0.f);
+      } else {
+        float* pp = a.attn_partial + ((size_t)bh * nsplit + split) * (DS_HD + 2);
+        __stcg(pp + 2 + wt, O);
+        if (wt == 0) { __stcg(pp, M); __stcg(pp + 1, Lsum); }
+      }
+    }
+    if (nsplit > 1) {
+      // the last split of (b, h) to arrive merges (tickets are zero on entry and left zero)
+      __threadfence();
+      ds_named_bar(2, DS_WORKERS);
+      if (wt == 0) sh.last = (atomicAdd(a.tickets + bh, 1) == nsplit - 1);
+      ds_named_bar(2, DS_WORKERS);
+      if (sh.last) {
+        __threadfence();
+        if (wt < DS_HD) {
+          const float* pp = a.attn_partial + (size_t)bh * nsplit * (DS_HD + 2);
+          float M2 = -CUDART_INF_F;
+          for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, __ldcg(pp + s2 * (DS_HD + 2)));
+          float L2 = 0.f, O2 = 0.f;
+          for (int s2 = 0; s2 < nsplit; ++s2) {
+            const float ms = __ldcg(pp + s2 * (DS_HD + 2));
+            const float w = (ms == -CUDART_INF_F) ? 0.f : ex2_approx(ms - M2);
+            L2 = fmaf(__ldcg(pp + s2 * (DS_HD + 2) + 1), w, L2);
+            O2 = fmaf(__ldcg(pp + s2 * (DS_HD + 2) + 2 + wt), w, O2);
+          }
+          reinterpret_cast<__nv_bfloat16*>(a.attn_out)[(size_t)b * HD + h * DS_HD + wt] = __float2bfloat16_rn(L2 > 0.f ? O2 / L2 : 0.f);
+        }
+        if (wt == 0) a.tickets[bh] = 0;
+      }
+    }
+    ds_named_bar(2, DS_WORKERS);               // sh.m / sh.l / sh.o are reused by the next item
+  }
+}
+
+__global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid_constant__ DsArgs a) {
+  extern __shared__ uint8_t ds_smem_raw[];
+  // SWIZZLE_128B atoms are 1024-byte aligned
+  uint8_t* smem = ds_smem_raw + ((1024u - (smem_u32(ds_smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = smem;                                        // DS_NSTAGES x 16 KB
+  uint8_t* xs = ring + DS_NSTAGES * DS_STAGE;                  // 2 x 32 KB
+  DsTask* tasks = reinterpret_cast<DsTask*>(xs + 2 * DS_XSLOT);
+  DsShared& sh = *reinterpret_cast<DsShared*>(reinterpret_cast<uint8_t*>(tasks) + (size_t)a.NP * sizeof(DsTask));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NP = a.NP;
+  // this CTA's row of the task table → shared memory (every role reads it, phase after phase)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.tasks + (size_t)blockIdx.x * NP);
+    uint4* dst = reinterpret_cast<uint4*>(tasks);
+    const int n16 = NP * (int)(sizeof(DsTask) / 16);
+    for (int i = tid; i < n16; i += DS_THREADS) dst[i] = __ldg(src + i);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < DS_NSTAGES; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
+    mbar_init(&sh.xfull[0], DS_WORKERS); mbar_init(&sh.xfull[1], DS_WORKERS);
+    mbar_init(&sh.xempty[0], 1); mbar_init(&sh.xempty[1], 1);
+    mbar_init(&sh.accfull, 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 256; i += DS_THREADS) sh.ss[i] = 0.f;
+  for (int i = tid; i < NP; i += DS_THREADS) sh.phase_kind[i] = __ldg(a.phase_kind + i);
+  if (warp == 1) {
+    tmem_alloc(&sh.tmem_base, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh.tmem_base;
+  const unsigned epoch0 = *a.epoch;
+  const int pos = min(*a.pos_dev, a.Tmax - 1);
+
+  if (warp == 0) {
+    // ===================== weight producer: this CTA's packed stream → ring, ahead of everything else =====================
+    // (the whole warp walks the loop and one elected lane issues: inside a `lane == 0` branch every uniform-datapath
+    //  instruction — UBLKCP, UTCHMMA, UTCBAR — is wrapped in a per-thread ELECT / R2UR loop of ~80 cycles)
+    const uint8_t* src = a.wstream + a.wstream_off[blockIdx.x];
+    uint32_t cnt = 0;
+    for (int p = 0; p < NP; ++p) {
+      const DsTask& t = tasks[p];
+      if (t.R == 0) continue;
+      const int slab = t.R * 128;
+      const int wkb = max(1, DS_STAGE / slab);
+      for (int j = 0; j < t.nkb; j += wkb) {
+        const int n = min(wkb, t.nkb - j);
+        const uint32_t bytes = (uint32_t)(n * slab);
+        const int s = cnt % DS_NSTAGES;
+        const uint32_t use = cnt / DS_NSTAGES;
+        if (use > 0) ds_mbar_wait(&sh.empty[s], (use - 1) & 1, a, 1, p);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sh.full[s], bytes);
+          ds_bulk_g2s(smem_u32(ring + s * DS_STAGE), src, bytes, &sh.full[s]);
+        }
+        __syncwarp();
+        src += bytes;
+        ++cnt;
+      }
+    }
+  } else {
+    uint32_t wcount = 0, xcount = 0, ntask = 0;       // ring stages / X slots / GEMM units consumed so far (role-local copies)
+    const uint32_t idesc = make_idesc_bf16(128, a.Bp, 0, 0);
+    // A chain of tcgen05.mma into ONE accumulator runs at ~150 cycles per instruction when N is small (measured: 16 MMAs of
+    // N = 16 took 2.4 k cycles); successive k steps therefore rotate over up to four accumulators that the epilogue sums.
+    const int nacc = a.Bp <= 64 ? 4 : (a.Bp == 128 ? 2 : 1);
+    const int cap = DS_XSLOT / (a.Bp * 128);
+    for (int p = 0; p < NP; ++p) {
+      const DsTask& t = tasks[p];
+      const int kind = sh.phase_kind[p];
+      if (kind >= 0) {
+        if (warp >= 2) ds_attention(a, sh, kind, pos, p);
+      } else if (t.R > 0) {
+        const int xkb = t.nkb < cap ? t.nkb : cap;
+        if (warp == 1) {
+          // ===================== MMA issuer =====================
+          const int slab = t.R * 128;
+          const int wkb = max(1, DS_STAGE / slab);
+          for (int j = 0; j < t.nkb; ++j) {
+            const int jw = j % wkb, jx = j % xkb;
+            const int s = wcount % DS_NSTAGES;
+            const int slot = xcount & 1;
+            if (jw == 0) ds_mbar_wait(&sh.full[s], (wcount / DS_NSTAGES) & 1, a, 2, p);
+            if (jx == 0) ds_mbar_wait(&sh.xfull[slot], (xcount >> 1) & 1, a, 3, p);
+            if (j == 0) DS_TRACE(6, 32);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(ring + s * DS_STAGE + jw * slab);
+            const uint32_t b_addr = smem_u32(xs + slot * DS_XSLOT + jx * (a.Bp * 128));
+            const bool w_done = (jw == wkb - 1 || j == t.nkb - 1), x_done = (jx == xkb - 1);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int kk = j * 4 + k;
+                umma_f16_ss(tmem_base + (uint32_t)((kk % nacc) * a.Bp), make_smem_desc_sw128(a_addr + k * 32, 16, 1024),
+                            make_smem_desc_sw128(b_addr + k * 32, 16, 1024), idesc, kk >= nacc);
+              }
+              if (w_done) umma_commit(&sh.empty[s]);
+              if (x_done) umma_commit(&sh.xempty[slot]);
+              if (j == t.nkb - 1) umma_commit(&sh.accfull);
+            }
+            __syncwarp();
+            if (j == 0) DS_TRACE(2, 32);
+            if (w_done) ++wcount;
+            if (x_done) ++xcount;
+          }
+          DS_TRACE(3, 32);
+        } else {
+          // ===================== workers: X operand, then (warps 4..7) the accumulator, (warps 2..3) auxiliary jobs ===========
+          ds_transform(a, t, sh, xs, xcount, p);
+          if (warp >= 4) {
+            const int q = warp - 4;
+            if (q * 32 < t.rows) {
+              ds_mbar_wait(&sh.accfull, ntask & 1, a, 4, p);
+              tc_fence_after();
+              DS_TRACE(4, 128);
+              const int r = q * 32 + lane;
+              const bool rv = r < t.rows;
+              const float badd = (rv && t.bias_out) ? __ldg(t.bias_out + t.n0 + r) : 0.f;
+              float* out = t.acc + t.n0 + r;
+              for (int c0 = 0; c0 < a.B; c0 += 16) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                tmem_ld_32x32b_x16(taddr, v);
+                if (nacc > 1) {
+                  uint32_t w1[16];
+                  tmem_ld_32x32b_x16(taddr + a.Bp, w1);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w1[i]));
+                  if (nacc > 2) {
+                    uint32_t w2[16], w3[16];
+                    tmem_ld_32x32b_x16(taddr + 2 * a.Bp, w2);
+                    tmem_ld_32x32b_x16(taddr + 3 * a.Bp, w3);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                      v[i] = __float_as_uint(__uint_as_float(v[i]) + (__uint_as_float(w2[i]) + __uint_as_float(w3[i])));
+                  }
+                }
+                tmem_ld_wait();
+                if (rv) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int b = c0 + i;
+                    if (b < a.B) {
+                      const float val = __uint_as_float(v[i]) + badd;
+                      if (t.store) __stcg(out + (size_t)b * t.ldacc, val);
+                      else ds_red_add(out + (size_t)b * t.ldacc, val);
+                    }
+                  }
+                }
+              }
+              tc_fence_before();
+              DS_TRACE(5, 128);
+            }
+          }
+        }
+        ++ntask;
+      }
+      if (t.aux_kind && (warp == 2 || warp == 3)) ds_aux(t);      // these two warps have no accumulator to drain
+      if (p + 1 < NP) ds_grid_barrier(a, epoch0 + (unsigned)p + 1u, p);
+    }
+  }
+  // ---- teardown: advance the launch epoch and the cache position for the next launch; free TMEM
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (blockIdx.x == 0 && tid == 0) {
+    // every CTA has read *epoch / *pos_dev before it could pass its first barrier, and this CTA is past the last one
+    *a.epoch = epoch0 + (unsigned)(NP - 1);                      // NP - 1 barriers per launch
+    if (a.advance_pos) *a.pos_dev = pos + 1;
+  }
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" size_t vg_decode_step_task_bytes(void) { return sizeof(vg_decode_step_task); }
+
+extern "C" size_t vg_decode_step_smem_bytes(int32_t n_phases) {
+  return 1024 + (size_t)DS_NSTAGES * DS_STAGE + 2 * DS_XSLOT + (size_t)n_phases * sizeof(vg_decode_step_task) +
+         sizeof(DsShared) + 64;
+}
+
+extern "C" int vg_decode_step(const vg_decode_step_args* a, vg_stream_t stream) {
+  VG_REQUIRE(a && a->tasks && a->phase_kind && a->wstream && a->wstream_off && a->epoch && a->pos_dev && a->bar_flags, -1,
+             "vg_decode_step: null pointer");
+  VG_REQUIRE(a->B >= 1 && a->B <= 256 && a->Bp >= 16 && a->Bp <= 256 && (a->Bp & (a->Bp - 1)) == 0 && a->Bp >= a->B, -3,
+             "vg_decode_step: batch %d / padded %d (power of two in [16,256])", a->B, a->Bp);
+  VG_REQUIRE(a->NP >= 1 && a->NP <= 128 && a->grid >= 1, -3, "vg_decode_step: bad phase count / grid");
+  VG_REQUIRE(a->nsplit >= 1 && a->nsplit <= 64, -3, "vg_decode_step: nsplit must be in [1,64]");
+  const size_t smem = vg_decode_step_smem_bytes(a->NP);
+  VG_REQUIRE(smem <= 227 * 1024, -6, "vg_decode_step: %d phases need %zu bytes of shared memory", a->NP, smem);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    VG_CUDA(cudaGetDevice(&dev));
+    VG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    VG_CUDA(cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  VG_REQUIRE(a->grid <= sms, -3, "vg_decode_step: grid %d exceeds the %d SMs (all CTAs must be co-resident)", a->grid, sms);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)a->grid);
+  cfg.blockDim = dim3(DS_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;       // co-residency of the whole grid is guaranteed or the launch fails
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VG_CUDA(cudaLaunchKernelEx(&cfg, decode_step_kernel, *a));
+  return 0;
+}

@@ -100,6 +100,9 @@ class LVTR(nn.Module):
         # ... up to this batch: measured on B200 (profiles/r01_decode.md) the weight-streaming engine wins up to ~100
         # sequences (0.47 vs 1.21 ms per step at B=1, 1.02 vs 1.37 at 64), the tcgen05 layer-by-layer path above
         self.decode_engine_max_batch = 96
+        # "step": the persistent single-launch kernel (decode_step.py, any batch <= 256); "linear": round 1's
+        # kernel-per-linear engine (decode.py, batch <= decode_engine_max_batch)
+        self.decode_engine_kind = "step"
 
     # ------------------------------------------------------------------ configuration
     def set_compute_dtype(self, dtype: torch.dtype) -> "LVTR":
@@ -322,15 +325,22 @@ class LVTR(nn.Module):
         from ...modules.attention.kvcache import LayerKV
         if (not self.use_decode_engine or u.shape[1] != 1 or c is not None or return_attn or return_distribution
                 or past_kv is None or not isinstance(past_kv[0], LayerKV) or not u.is_cuda
-                or self.compute_dtype != torch.bfloat16 or u.shape[0] > self.decode_engine_max_batch):
+                or self.compute_dtype != torch.bfloat16):
             return None
-        from ...decode import DecodeEngine
+        step_kind = self.decode_engine_kind == "step"
+        if u.shape[0] > (256 if step_kind else self.decode_engine_max_batch):
+            return None
         engines = self.__dict__.setdefault("_decode_engines", {})
         stack = self.transformer[0]
-        stamp = tuple(p._version for p in stack.parameters())     # rebuilt when the weights have been updated
+        stamp = (self.decode_engine_kind,) + tuple(p._version for p in stack.parameters())   # rebuilt after a weight update
         ent = engines.get(u.shape[0])
         if ent is None or ent[0] != stamp:
-            ent = (stamp, DecodeEngine(self, u.shape[0], u.device))
+            if step_kind:
+                from ...decode_step import DecodeStepEngine
+                ent = (stamp, DecodeStepEngine(self, u.shape[0], u.device))
+            else:
+                from ...decode import DecodeEngine
+                ent = (stamp, DecodeEngine(self, u.shape[0], u.device))
             engines[u.shape[0]] = ent
         return ent[1]
 
