@@ -44,14 +44,17 @@ constexpr long long DS_TIMEOUT = 4000000000LL;      // ~2 s of SM clocks
 typedef vg_decode_step_task DsTask;
 typedef vg_decode_step_args DsArgs;
 
+constexpr int DS_VEC_MAX = 1024;           // floats of a unit's per-k vector (RMSNorm scale / bias) prefetched into shared memory
+constexpr int DS_BIAS_MAX = 128;           // floats of a unit's output bias (R <= 128)
+
 struct DsShared {
   uint64_t full[DS_NSTAGES], empty[DS_NSTAGES], xfull[2], xempty[2], accfull;
   uint32_t tmem_base;
-  int last;
-  float m[DS_GROUPS], l[DS_GROUPS];
-  float o[DS_GROUPS][DS_HD];
+  int last[DS_WORKERS / 32];
   float ss[256];
   int phase_kind[128];
+  __align__(16) float vec[2][DS_VEC_MAX];
+  __align__(16) float bias[2][DS_BIAS_MAX];
 };
 
 __device__ __forceinline__ void ds_die(const DsArgs& a, int code, int phase) {
@@ -88,83 +91,86 @@ __device__ __forceinline__ void ds_bulk_g2s(uint32_t smem_dst, const void* gsrc,
 __device__ __forceinline__ void ds_red_add(float* p, float v) {
   asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+__device__ __forceinline__ void ds_red_add4(float* p, float x, float y, float z, float w) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void ds_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ds_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ds_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ds_pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ float ds_round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
-
-// ---- device-wide barrier (warps 1..7; the producer warp never stops).  mode 0: every CTA publishes the epoch in its own
-// flag word and one warp polls all flags (no atomics, no same-address serialisation); mode 1: one monotonic counter.
-__device__ __forceinline__ void ds_grid_barrier(const DsArgs& a, unsigned epoch, int phase) {
-  ds_named_bar(1, DS_THREADS - 32);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (a.trace && threadIdx.x == 32) a.trace[((size_t)blockIdx.x * a.NP + phase) * 8] = clock64();
-  if (warp == 1) {
-    const unsigned G = gridDim.x;
-    if (a.barrier_mode == 0) {
-      if (lane == 0) {
-        __threadfence();
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.bar_flags + blockIdx.x), "r"(epoch) : "memory");
-      }
-      const long long t0 = clock64();
-      for (;;) {
-        bool ok = true;
-        for (unsigned i = lane; i < G; i += 32) ok = ok & ((int)(ds_ld_relaxed(a.bar_flags + i) - epoch) >= 0);
-        if (__all_sync(0xffffffffu, ok)) break;
-        if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 100, phase);
-      }
-      __threadfence();
-    } else if (a.barrier_mode == 1) {
-      if (lane == 0) {
-        __threadfence();
-        atomicAdd(a.bar_flags, 1u);
-        const unsigned target = epoch * G;
-        const long long t0 = clock64();
-        while ((int)(ds_ld_acquire(a.bar_flags) - target) < 0)
-          if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 101, phase);
-        __threadfence();
-      }
-    } else {
-      // mode 2: flags gathered by CTA 0 (148 loads per poll round instead of 148 x 148 on one L2 slice), which publishes
-      // one "go" word (a different cache line) that everybody else polls
-      unsigned* go = a.bar_flags + ((G + 63u) & ~31u);
-      if (lane == 0) {
-        __threadfence();
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.bar_flags + blockIdx.x), "r"(epoch) : "memory");
-      }
-      const long long t0 = clock64();
-      if (blockIdx.x == 0) {
-        for (;;) {
-          bool ok = true;
-          for (unsigned i = lane; i < G; i += 32) ok = ok & ((int)(ds_ld_relaxed(a.bar_flags + i) - epoch) >= 0);
-          if (__all_sync(0xffffffffu, ok)) break;
-          if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 102, phase);
-        }
-        __threadfence();
-        if (lane == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(epoch) : "memory");
-      } else {
-        if (lane == 0) {
-          while ((int)(ds_ld_relaxed(go) - epoch) < 0)
-            if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 103, phase);
-        }
-        __syncwarp();
-        __threadfence();
-      }
-    }
-  }
-  if (a.trace && threadIdx.x == 32) a.trace[((size_t)blockIdx.x * a.NP + phase) * 8 + 1] = clock64();
-  ds_named_bar(1, DS_THREADS - 32);
 }
 
 #define DS_TRACE(slot, thread) \
   do { if (a.trace && threadIdx.x == (thread)) a.trace[((size_t)blockIdx.x * a.NP + p) * 8 + (slot)] = clock64(); } while (0)
 
+// ---- device-wide barrier (warps 1..7; the producer warp never stops).
+//   mode 1: one monotonic counter — red.release.gpu by one thread per CTA, the same thread polls with ld.acquire.gpu
+//   mode 2: per-CTA flag words gathered by CTA 0, which publishes one "go" word that the other CTAs poll
+// (every CTA polling every flag, 148 x 148 loads per round on one L2 slice, was 2x slower than either: profiles/r02_decode.md)
+__device__ __forceinline__ void ds_grid_barrier(const DsArgs& a, unsigned epoch, int phase) {
+  const int p = phase;
+  ds_named_bar(1, DS_THREADS - 32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DS_TRACE(0, 32);
+  if (warp == 1) {
+    const unsigned G = gridDim.x;
+    if (a.barrier_mode == 1) {
+      if (lane == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(a.bar_flags), "r"(1u) : "memory");
+        const unsigned target = epoch * G;
+        const long long t0 = clock64();
+        while ((int)(ds_ld_acquire(a.bar_flags) - target) < 0)
+          if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 101, phase);
+      }
+    } else {
+      unsigned* go = a.bar_flags + ((G + 63u) & ~31u);
+      if (lane == 0)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.bar_flags + blockIdx.x), "r"(epoch) : "memory");
+      const long long t0 = clock64();
+      if (blockIdx.x == 0) {
+        for (;;) {
+          bool ok = true;
+          for (unsigned i = lane; i < G; i += 32) ok = ok & ((int)(ds_ld_acquire(a.bar_flags + i) - epoch) >= 0);
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 102, phase);
+        }
+        if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(epoch) : "memory");
+      } else if (lane == 0) {
+        while ((int)(ds_ld_acquire(go) - epoch) < 0)
+          if (clock64() - t0 > DS_TIMEOUT) ds_die(a, 103, phase);
+      }
+    }
+  }
+  DS_TRACE(1, 32);
+  ds_named_bar(1, DS_THREADS - 32);
+}
+
+// ---- per-k vector (RMSNorm scale / bias of the X transform) and output bias of a unit → shared memory, ahead of time:
+// these 33 + 35 vectors are touched once per step, and the 408 MB weight stream evicts them from L2 in between, so a plain
+// load in the transform is an HBM miss on the critical path of every phase.  Issued by warps 2..3 with cp.async right after
+// the previous unit's transform; waited for at the start of the unit's own transform.
+__device__ __forceinline__ bool ds_vec_prefetched(const DsTask& t) { return t.vec != nullptr && t.nkb * 64 <= DS_VEC_MAX; }
+__device__ __forceinline__ void ds_prefetch_vec(const DsTask& t, DsShared& sh, int par) {
+  const int at = threadIdx.x - 64;              // 0..63
+  if (ds_vec_prefetched(t))
+    for (int i = at; i < t.nkb * 16; i += 64) ds_cp_async16(&sh.vec[par][i * 4], t.vec + t.k0 + i * 4);
+  if (t.bias_out)
+    for (int i = at; i < t.R / 4; i += 64) ds_cp_async16(&sh.bias[par][i * 4], t.bias_out + t.n0 + i * 4);
+  ds_cp_async_commit();
+}
+
 // ---- X operand: worker warps form the bf16, SWIZZLE_128B K-major [Bp x 64] tiles of this unit's k-range.
 //   kind 0: x bf16 [B, ldx] as is          kind 1: x f32 * vec[k]   (RMSNorm scale; 1/rms is applied by the consumer of the sums)
 //   kind 2: act(x f32 * rstd[b] + vec[k])  (rstd from the row sum-of-squares the kind-1 phase accumulated)
+// Items of 8 consecutive k of one batch row; a thread loads DS_XU items before it touches any of them (the sources are
+// L2-resident accumulators: one dependent L2 round trip per item would be the whole cost of the transform).
+constexpr int DS_XU = 4;
 __device__ __forceinline__ void ds_transform(const DsArgs& a, const DsTask& t, DsShared& sh, uint8_t* xs, uint32_t& xcount,
-                                             int phase) {
+                                             int par, int phase) {
   const int p = phase;
   const int wt = threadIdx.x - 64;
   const int lane = threadIdx.x & 31;
@@ -176,51 +182,77 @@ __device__ __forceinline__ void ds_transform(const DsArgs& a, const DsTask& t, D
   const int items = B * per_b;
   const int items_pad = (items + 31) & ~31;
   const bool want_ss = t.ss_out != nullptr;
+  const bool vec_smem = ds_vec_prefetched(t);
+  if (wt < 64) ds_cp_async_wait_all();          // the prefetch of this unit's vectors (issued by these two warps)
+  ds_named_bar(2, DS_WORKERS);
   for (int c = 0; c < nchunks; ++c) {
     const int slot = xcount & 1;
     const uint32_t use = xcount >> 1;
     if (use > 0) ds_mbar_wait(&sh.xempty[slot], (use - 1) & 1, a, 10, phase);
     uint8_t* dst = xs + slot * DS_XSLOT;
-    for (int item = wt; item < items_pad; item += DS_WORKERS) {
-      float ssq = 0.f;
-      int b = 0;
-      if (item < items) {
-        b = item / per_b;
-        const int rem = item - b * per_b;
-        const int j = rem >> 3, g = rem & 7;
-        const int k = t.k0 + (c * xkb + j) * 64 + g * 8;
-        uint4 packed;
-        if (t.x_kind == 0) {
-          packed = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t.x) + (size_t)b * t.ldx + k));
-        } else {
-          const float* src = reinterpret_cast<const float*>(t.x) + (size_t)b * t.ldx + k;
-          const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src));
-          const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src) + 1);
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(t.vec + k));
-          const float4 s1 = __ldg(reinterpret_cast<const float4*>(t.vec + k) + 1);
-          float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          if (t.x_kind == 1) {
+    for (int base = wt; base < items_pad; base += DS_WORKERS * DS_XU) {
+      uint4 raw0[DS_XU], raw1[DS_XU];
+      float ssv[DS_XU];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { ssq = fmaf(v[i], v[i], ssq); v[i] *= s[i]; }
+      for (int u = 0; u < DS_XU; ++u) {
+        const int item = base + u * DS_WORKERS;
+        ssv[u] = 0.f;
+        if (item < items) {
+          const int b = item / per_b;
+          const int rem = item - b * per_b;
+          const int k = t.k0 + (c * xkb + (rem >> 3)) * 64 + (rem & 7) * 8;
+          if (t.x_kind == 0) {
+            raw0[u] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t.x) + (size_t)b * t.ldx + k));
           } else {
-            const float rstd = t.ss_in ? rsqrtf(__ldcg(t.ss_in + b) * t.inv_k + t.eps) : 1.0f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float y = fmaf(v[i], rstd, s[i]);
-              v[i] = t.act == VG_ACT_GELU ? gelu_fast(y) : (t.act == VG_ACT_RELU ? fmaxf(y, 0.f) : y);
-            }
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(t.x) + (size_t)b * t.ldx + k);
+            raw0[u] = __ldcg(src);
+            raw1[u] = __ldcg(src + 1);
+            if (t.x_kind == 2 && t.ss_in) ssv[u] = __ldcg(t.ss_in + b);
           }
-          packed.x = ds_pack_bf16(v[0], v[1]); packed.y = ds_pack_bf16(v[2], v[3]);
-          packed.z = ds_pack_bf16(v[4], v[5]); packed.w = ds_pack_bf16(v[6], v[7]);
         }
-        *reinterpret_cast<uint4*>(dst + j * (Bp * 128) + (b >> 3) * 1024 + (b & 7) * 128 + ((g ^ (b & 7)) << 4)) = packed;
       }
-      if (want_ss) {
-        // lanes of one batch row are contiguous: per_b (a power of two >= 8) lanes per row when per_b < 32, else whole warps
-        const int seg = per_b < 32 ? per_b : 32;
-        for (int o = 1; o < seg; o <<= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
-        if ((lane & (seg - 1)) == 0 && item < items) atomicAdd(&sh.ss[b], ssq);
+#pragma unroll
+      for (int u = 0; u < DS_XU; ++u) {
+        const int item = base + u * DS_WORKERS;
+        if (item >= items_pad) break;             // warp-uniform: items_pad is a multiple of 32
+        float ssq = 0.f;
+        int b = 0;
+        if (item < items) {
+          b = item / per_b;
+          const int rem = item - b * per_b;
+          const int j = rem >> 3, g = rem & 7;
+          uint4 packed = raw0[u];
+          if (t.x_kind != 0) {
+            const int kl = (c * xkb + j) * 64 + g * 8;                 // k relative to the unit's k0
+            const float4* vp = vec_smem ? reinterpret_cast<const float4*>(&sh.vec[par][kl])
+                                        : reinterpret_cast<const float4*>(t.vec + t.k0 + kl);
+            const float4 s0 = vp[0], s1 = vp[1];
+            float v[8] = {__uint_as_float(raw0[u].x), __uint_as_float(raw0[u].y), __uint_as_float(raw0[u].z),
+                          __uint_as_float(raw0[u].w), __uint_as_float(raw1[u].x), __uint_as_float(raw1[u].y),
+                          __uint_as_float(raw1[u].z), __uint_as_float(raw1[u].w)};
+            const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            if (t.x_kind == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { ssq = fmaf(v[i], v[i], ssq); v[i] *= s[i]; }
+            } else {
+              const float rstd = t.ss_in ? rsqrtf(ssv[u] * t.inv_k + t.eps) : 1.0f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float y = fmaf(v[i], rstd, s[i]);
+                v[i] = t.act == VG_ACT_GELU ? gelu_fast(y) : (t.act == VG_ACT_RELU ? fmaxf(y, 0.f) : y);
+              }
+            }
+            packed.x = ds_pack_bf16(v[0], v[1]); packed.y = ds_pack_bf16(v[2], v[3]);
+            packed.z = ds_pack_bf16(v[4], v[5]); packed.w = ds_pack_bf16(v[6], v[7]);
+          }
+          *reinterpret_cast<uint4*>(dst + j * (Bp * 128) + (b >> 3) * 1024 + (b & 7) * 128 + ((g ^ (b & 7)) << 4)) = packed;
+        }
+        if (want_ss) {
+          // lanes of one batch row are contiguous: per_b (a power of two >= 8) lanes per row when per_b < 32, else whole warps
+          const int seg = per_b < 32 ? per_b : 32;
+          for (int o = 1; o < seg; o <<= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+          if ((lane & (seg - 1)) == 0 && item < items) atomicAdd(&sh.ss[b], ssq);
+        }
       }
     }
     fence_proxy_async();
@@ -269,20 +301,25 @@ __device__ __forceinline__ void ds_aux(const DsTask& t) {
   }
 }
 
-// ---- attention phase: items (b, h, split) over the head-major KV cache; the new token's k / v come from the QKV sums
+// ---- attention phase: items (b, h, split), ONE WARP per item (no CTA-level barriers inside the phase); 8 lanes share a
+// key row (16-byte loads: a warp instruction covers 4 full 128-byte rows), DS_KU x 4 keys of K and V in flight per warp,
+// online softmax per 8-lane group in the exp2 domain, groups merged with shuffles; with nsplit > 1 the last warp of a
+// (b, h) to arrive (ticket) merges the partials.  The new token's k / v come from the QKV sums of the phase before (· 1/rms,
+// rounded to bf16 — the value that goes into the cache) and are appended here.
+constexpr int DS_KU = 8;
 __device__ __forceinline__ void ds_attention(const DsArgs& a, DsShared& sh, int layer, int pos, int phase) {
-  const int wt = threadIdx.x - 64;
+  const int ww = (threadIdx.x >> 5) - 2;        // 0..5
   const int lane = threadIdx.x & 31;
-  const int grp = (wt >> 5) * 4 + (lane >> 3);
-  const int sub = lane & 7;
+  const int grp = lane >> 3, sub = lane & 7;
   const int H = a.H, HD = a.H * DS_HD;
   const int nsplit = a.nsplit;
   const int n_items = a.B * H * nsplit;
   const int nkeys = pos + 1;
   const int chunk = (nkeys + nsplit - 1) / nsplit;
   const float* ss = a.ss_base + (size_t)(2 * layer) * a.B;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.attn_out);
   constexpr float LOG2E = 1.4426950408889634f;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  for (int item = blockIdx.x * (DS_WORKERS / 32) + ww; item < n_items; item += gridDim.x * (DS_WORKERS / 32)) {
     const int split = item % nsplit;
     const int bh = item / nsplit;
     const int h = bh % H, b = bh / H;
@@ -296,24 +333,24 @@ __device__ __forceinline__ void ds_attention(const DsArgs& a, DsShared& sh, int 
       q[0] = q0.x * f; q[1] = q0.y * f; q[2] = q0.z * f; q[3] = q0.w * f;
       q[4] = q1.x * f; q[5] = q1.y * f; q[6] = q1.z * f; q[7] = q1.w * f;
     }
-    const float slope = (a.slopes ? a.slopes[h] : 0.f) * LOG2E;
-    __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(a.cache) + (size_t)layer * a.cache_layer_stride + ((size_t)b * H + h) * (size_t)a.Tmax * DS_HD;
+    const float slope = (a.slopes ? __ldg(a.slopes + h) : 0.f) * LOG2E;
+    __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(a.cache) + (size_t)layer * a.cache_layer_stride +
+                        ((size_t)b * H + h) * (size_t)a.Tmax * DS_HD;
     __nv_bfloat16* vc = kc + a.cache_kv_stride;
     const int j_begin = split * chunk;
     const int j_end = min(nkeys, j_begin + chunk);
     float m = -CUDART_INF_F, l = 0.f, acc[8];
 #pragma unroll
     for (int d = 0; d < 8; ++d) acc[d] = 0.f;
-    for (int base = j_begin; base < j_end; base += DS_GROUPS * DS_KUNROLL) {
-      uint4 kraw[DS_KUNROLL], vraw[DS_KUNROLL];
+    for (int base = j_begin; base < j_end; base += 4 * DS_KU) {
+      uint4 kraw[DS_KU], vraw[DS_KU];
 #pragma unroll
-      for (int u = 0; u < DS_KUNROLL; ++u) {
-        const int j = base + u * DS_GROUPS + grp;
+      for (int u = 0; u < DS_KU; ++u) {
+        const int j = base + u * 4 + grp;
         if (j < j_end && j != pos) {
           kraw[u] = __ldcs(reinterpret_cast<const uint4*>(kc + (size_t)j * DS_HD + sub * 8));
           vraw[u] = __ldcs(reinterpret_cast<const uint4*>(vc + (size_t)j * DS_HD + sub * 8));
         } else if (j == pos && j < j_end) {
-          // the new token: k, v = bf16(sum * rstd) of this step's QKV accumulators; appended to the cache here
           const float4 k0 = __ldcg(reinterpret_cast<const float4*>(row + HD));
           const float4 k1 = __ldcg(reinterpret_cast<const float4*>(row + HD) + 1);
           const float4 v0 = __ldcg(reinterpret_cast<const float4*>(row + 2 * HD));
@@ -330,8 +367,8 @@ __device__ __forceinline__ void ds_attention(const DsArgs& a, DsShared& sh, int 
         }
       }
 #pragma unroll
-      for (int u = 0; u < DS_KUNROLL; ++u) {
-        const int j = base + u * DS_GROUPS + grp;
+      for (int u = 0; u < DS_KU; ++u) {
+        const int j = base + u * 4 + grp;
         const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kraw[u]);
         float s = 0.f;
 #pragma unroll
@@ -360,55 +397,59 @@ __device__ __forceinline__ void ds_attention(const DsArgs& a, DsShared& sh, int 
         }
       }
     }
-    if (sub == 0) { sh.m[grp] = m; sh.l[grp] = l; }
+    // merge the four 8-lane groups (same sub = same head dims): lanes 0..7 end up with the warp's result
 #pragma unroll
-    for (int d = 0; d < 8; ++d) sh.o[grp][sub * 8 + d] = acc[d];
-    ds_named_bar(2, DS_WORKERS);
-    float M = -CUDART_INF_F, Lsum = 0.f, O = 0.f;
-    if (wt < DS_HD) {
+    for (int off = 8; off <= 16; off <<= 1) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+      const float lo = __shfl_xor_sync(0xffffffffu, l, off);
+      const float mn = fmaxf(m, mo);
+      const float wa = (m == -CUDART_INF_F) ? 0.f : ex2_approx(m - mn);
+      const float wb = (mo == -CUDART_INF_F) ? 0.f : ex2_approx(mo - mn);
+      l = l * wa + lo * wb;
 #pragma unroll
-      for (int g = 0; g < DS_GROUPS; ++g) M = fmaxf(M, sh.m[g]);
-      if (M != -CUDART_INF_F) {
-#pragma unroll
-        for (int g = 0; g < DS_GROUPS; ++g) {
-          const float w = (sh.m[g] == -CUDART_INF_F) ? 0.f : ex2_approx(sh.m[g] - M);
-          Lsum = fmaf(sh.l[g], w, Lsum);
-          O = fmaf(sh.o[g][wt], w, O);
-        }
-      }
-      if (nsplit == 1) {
-        reinterpret_cast<__nv_bfloat16*>(a.attn_out)[(size_t)b * HD + h * DS_HD + wt] = __float2bfloat16_rn(Lsum > 0.f ? O / Lsum : 0.f);
-      } else {
-        float* pp = a.attn_partial + ((size_t)bh * nsplit + split) * (DS_HD + 2);
-        __stcg(pp + 2 + wt, O);
-        if (wt == 0) { __stcg(pp, M); __stcg(pp + 1, Lsum); }
-      }
+      for (int d = 0; d < 8; ++d) acc[d] = acc[d] * wa + __shfl_xor_sync(0xffffffffu, acc[d], off) * wb;
+      m = mn;
     }
-    if (nsplit > 1) {
+    if (nsplit == 1) {
+      if (grp == 0) {
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        uint4 o;
+        o.x = ds_pack_bf16(acc[0] * inv, acc[1] * inv); o.y = ds_pack_bf16(acc[2] * inv, acc[3] * inv);
+        o.z = ds_pack_bf16(acc[4] * inv, acc[5] * inv); o.w = ds_pack_bf16(acc[6] * inv, acc[7] * inv);
+        *reinterpret_cast<uint4*>(out + (size_t)b * HD + h * DS_HD + sub * 8) = o;
+      }
+    } else {
+      float* pp = a.attn_partial + ((size_t)bh * nsplit + split) * (DS_HD + 8);      // [m, l, pad.., o[64]] 16-byte aligned rows
+      if (grp == 0) {
+        __stcg(reinterpret_cast<float4*>(pp + 8 + sub * 8), make_float4(acc[0], acc[1], acc[2], acc[3]));
+        __stcg(reinterpret_cast<float4*>(pp + 8 + sub * 8) + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
+        if (sub == 0) __stcg(reinterpret_cast<float2*>(pp), make_float2(m, l));
+      }
       // the last split of (b, h) to arrive merges (tickets are zero on entry and left zero)
       __threadfence();
-      ds_named_bar(2, DS_WORKERS);
-      if (wt == 0) sh.last = (atomicAdd(a.tickets + bh, 1) == nsplit - 1);
-      ds_named_bar(2, DS_WORKERS);
-      if (sh.last) {
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) last = (atomicAdd(a.tickets + bh, 1) == nsplit - 1);
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
         __threadfence();
-        if (wt < DS_HD) {
-          const float* pp = a.attn_partial + (size_t)bh * nsplit * (DS_HD + 2);
-          float M2 = -CUDART_INF_F;
-          for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, __ldcg(pp + s2 * (DS_HD + 2)));
-          float L2 = 0.f, O2 = 0.f;
-          for (int s2 = 0; s2 < nsplit; ++s2) {
-            const float ms = __ldcg(pp + s2 * (DS_HD + 2));
-            const float w = (ms == -CUDART_INF_F) ? 0.f : ex2_approx(ms - M2);
-            L2 = fmaf(__ldcg(pp + s2 * (DS_HD + 2) + 1), w, L2);
-            O2 = fmaf(__ldcg(pp + s2 * (DS_HD + 2) + 2 + wt), w, O2);
-          }
-          reinterpret_cast<__nv_bfloat16*>(a.attn_out)[(size_t)b * HD + h * DS_HD + wt] = __float2bfloat16_rn(L2 > 0.f ? O2 / L2 : 0.f);
+        const float* p0 = a.attn_partial + (size_t)bh * nsplit * (DS_HD + 8);
+        float M2 = -CUDART_INF_F;
+        for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, __ldcg(p0 + s2 * (DS_HD + 8)));
+        float L2 = 0.f, o0 = 0.f, o1 = 0.f;
+        for (int s2 = 0; s2 < nsplit; ++s2) {
+          const float2 ml = __ldcg(reinterpret_cast<const float2*>(p0 + s2 * (DS_HD + 8)));
+          const float w = (ml.x == -CUDART_INF_F) ? 0.f : ex2_approx(ml.x - M2);
+          const float2 ov = __ldcg(reinterpret_cast<const float2*>(p0 + s2 * (DS_HD + 8) + 8 + lane * 2));
+          L2 = fmaf(ml.y, w, L2);
+          o0 = fmaf(ov.x, w, o0);
+          o1 = fmaf(ov.y, w, o1);
         }
-        if (wt == 0) a.tickets[bh] = 0;
+        const float inv = L2 > 0.f ? 1.0f / L2 : 0.f;
+        *reinterpret_cast<uint32_t*>(out + (size_t)b * HD + h * DS_HD + lane * 2) = ds_pack_bf16(o0 * inv, o1 * inv);
+        if (lane == 0) a.tickets[bh] = 0;
       }
     }
-    ds_named_bar(2, DS_WORKERS);               // sh.m / sh.l / sh.o are reused by the next item
   }
 }
 
@@ -478,11 +519,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
     }
   } else {
     uint32_t wcount = 0, xcount = 0, ntask = 0;       // ring stages / X slots / GEMM units consumed so far (role-local copies)
-    const uint32_t idesc = make_idesc_bf16(128, a.Bp, 0, 0);
-    // A chain of tcgen05.mma into ONE accumulator runs at ~150 cycles per instruction when N is small (measured: 16 MMAs of
-    // N = 16 took 2.4 k cycles); successive k steps therefore rotate over up to four accumulators that the epilogue sums.
-    const int nacc = a.Bp <= 64 ? 4 : (a.Bp == 128 ? 2 : 1);
     const int cap = DS_XSLOT / (a.Bp * 128);
+    const int mtiles = a.Bp > 128 ? 2 : 1;            // 128 batch rows per tcgen05 M tile
+    int pnext = 0;                                    // next phase whose unit's vectors have not been prefetched yet
+    if (warp == 2 || warp == 3) {
+      while (pnext < NP && tasks[pnext].R == 0) ++pnext;
+      if (pnext < NP) ds_prefetch_vec(tasks[pnext], sh, 0);
+      ++pnext;
+    }
     for (int p = 0; p < NP; ++p) {
       const DsTask& t = tasks[p];
       const int kind = sh.phase_kind[p];
@@ -490,8 +534,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
         if (warp >= 2) ds_attention(a, sh, kind, pos, p);
       } else if (t.R > 0) {
         const int xkb = t.nkb < cap ? t.nkb : cap;
+        const int par = ntask & 1;
         if (warp == 1) {
-          // ===================== MMA issuer =====================
+          // ===================== MMA issuer: D[batch rows x R features] += X[128 x 64] · W_slab[R x 64]ᵀ per k-block ==========
+          // (the batch is the M operand: the accumulator row of a thread is a batch row, its columns are consecutive
+          //  features — contiguous in the row-major accumulators, so the epilogue reduces with 16-byte vector atomics)
+          const uint32_t idesc = make_idesc_bf16(128, t.R, 0, 0);
           const int slab = t.R * 128;
           const int wkb = max(1, DS_STAGE / slab);
           for (int j = 0; j < t.nkb; ++j) {
@@ -502,15 +550,15 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             if (jx == 0) ds_mbar_wait(&sh.xfull[slot], (xcount >> 1) & 1, a, 3, p);
             if (j == 0) DS_TRACE(6, 32);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(ring + s * DS_STAGE + jw * slab);
-            const uint32_t b_addr = smem_u32(xs + slot * DS_XSLOT + jx * (a.Bp * 128));
+            const uint32_t w_addr = smem_u32(ring + s * DS_STAGE + jw * slab);
+            const uint32_t x_addr = smem_u32(xs + slot * DS_XSLOT + jx * (a.Bp * 128));
             const bool w_done = (jw == wkb - 1 || j == t.nkb - 1), x_done = (jx == xkb - 1);
             if (elect_one()) {
+              for (int mt = 0; mt < mtiles; ++mt) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int kk = j * 4 + k;
-                umma_f16_ss(tmem_base + (uint32_t)((kk % nacc) * a.Bp), make_smem_desc_sw128(a_addr + k * 32, 16, 1024),
-                            make_smem_desc_sw128(b_addr + k * 32, 16, 1024), idesc, kk >= nacc);
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_ss(tmem_base + (uint32_t)(mt * t.R), make_smem_desc_sw128(x_addr + mt * 16384 + k * 32, 16, 1024),
+                              make_smem_desc_sw128(w_addr + k * 32, 16, 1024), idesc, (j | k) != 0);
               }
               if (w_done) umma_commit(&sh.empty[s]);
               if (x_done) umma_commit(&sh.xempty[slot]);
@@ -523,47 +571,35 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           }
           DS_TRACE(3, 32);
         } else {
-          // ===================== workers: X operand, then (warps 4..7) the accumulator, (warps 2..3) auxiliary jobs ===========
-          ds_transform(a, t, sh, xs, xcount, p);
+          // ===================== workers: X operand, then (warps 4..7) the accumulator, (warps 2..3) prefetch + aux ==========
+          ds_transform(a, t, sh, xs, xcount, par, p);
           if (warp >= 4) {
             const int q = warp - 4;
-            if (q * 32 < t.rows) {
+            if (q * 32 < a.B) {
               ds_mbar_wait(&sh.accfull, ntask & 1, a, 4, p);
               tc_fence_after();
               DS_TRACE(4, 128);
-              const int r = q * 32 + lane;
-              const bool rv = r < t.rows;
-              const float badd = (rv && t.bias_out) ? __ldg(t.bias_out + t.n0 + r) : 0.f;
-              float* out = t.acc + t.n0 + r;
-              for (int c0 = 0; c0 < a.B; c0 += 16) {
-                uint32_t v[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-                tmem_ld_32x32b_x16(taddr, v);
-                if (nacc > 1) {
-                  uint32_t w1[16];
-                  tmem_ld_32x32b_x16(taddr + a.Bp, w1);
+              for (int mt = 0; mt < mtiles; ++mt) {
+                const int b = mt * 128 + q * 32 + lane;
+                if (mt * 128 + q * 32 >= a.B) break;
+                float* orow = t.acc + (size_t)b * t.ldacc + t.n0;
+                for (int c0 = 0; c0 < t.rows; c0 += 16) {
+                  uint32_t v[16];
+                  tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * t.R + c0), v);
                   tmem_ld_wait();
+                  if (b < a.B) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w1[i]));
-                  if (nacc > 2) {
-                    uint32_t w2[16], w3[16];
-                    tmem_ld_32x32b_x16(taddr + 2 * a.Bp, w2);
-                    tmem_ld_32x32b_x16(taddr + 3 * a.Bp, w3);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                      v[i] = __float_as_uint(__uint_as_float(v[i]) + (__uint_as_float(w2[i]) + __uint_as_float(w3[i])));
-                  }
-                }
-                tmem_ld_wait();
-                if (rv) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    const int b = c0 + i;
-                    if (b < a.B) {
-                      const float val = __uint_as_float(v[i]) + badd;
-                      if (t.store) __stcg(out + (size_t)b * t.ldacc, val);
-                      else ds_red_add(out + (size_t)b * t.ldacc, val);
+                    for (int g = 0; g < 4; ++g) {
+                      if (c0 + 4 * g < t.rows) {            // rows is a multiple of 4
+                        float4 val = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                                 __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+                        if (t.bias_out) {
+                          const float4 bb = *reinterpret_cast<const float4*>(&sh.bias[par][c0 + 4 * g]);
+                          val.x += bb.x; val.y += bb.y; val.z += bb.z; val.w += bb.w;
+                        }
+                        if (t.store) __stcg(reinterpret_cast<float4*>(orow + c0 + 4 * g), val);
+                        else ds_red_add4(orow + c0 + 4 * g, val.x, val.y, val.z, val.w);
+                      }
                     }
                   }
                 }
@@ -571,6 +607,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
               tc_fence_before();
               DS_TRACE(5, 128);
             }
+          } else {
+            // the NEXT unit's vectors, into the other buffer (this unit's bias is still being read by the epilogue warps)
+            while (pnext < NP && tasks[pnext].R == 0) ++pnext;
+            if (pnext < NP) ds_prefetch_vec(tasks[pnext], sh, par ^ 1);
+            ++pnext;
           }
         }
         ++ntask;

@@ -39,8 +39,8 @@ TASK_DTYPE = np.dtype([
 
 
 def _rows_per_unit(N: int, S: int, units: int = UNITS) -> int:
-    """output features per unit (multiple of 8) so that ceil(N / R) * S is about ``units``"""
-    return max(8, (-(-(N * S) // units) + 7) // 8 * 8)
+    """output features per unit (multiple of 16: the N of a tcgen05 M=128 tile) so that ceil(N / R) * S is about ``units``"""
+    return max(16, (-(-(N * S) // units) + 15) // 16 * 16)
 
 
 def split_factor(N: int, K: int, units: int = UNITS, max_split: int = 16) -> Tuple[int, int]:
@@ -78,6 +78,19 @@ def pack_units(W: torch.Tensor, R: int, S: int) -> torch.Tensor:
     src_g = (r[:, None] ^ r[None, :])                              # position g' of row r holds source group g' ^ r
     v = v[:, :, :, :, r[:, None], src_g, :]                        # slab, s, kb, rg, r, g', e
     return v.contiguous().view(n_slabs, S, nkb * R * 64)
+
+
+def attention_splits(n_bh: int, n_warps: int) -> int:
+    """kv-splits per (sequence, head) for the attention phases: items = n_bh * splits are dealt round-robin to the
+    ``n_warps`` worker warps of the grid (one warp per item).  Few (b, h): about half a wave of short items (the merge of
+    the partials by the last arriver grows with the split count); many: the smallest split whose last wave is >= 85 % full."""
+    if n_bh * 2 <= n_warps:
+        return max(1, min(64, n_warps // (2 * n_bh)))
+    for s in (1, 2, 4, 8, 16):
+        items = n_bh * s
+        if items / (-(-items // n_warps) * n_warps) >= 0.85:
+            return s
+    return 16
 
 
 class _Args(C.Structure):
@@ -282,15 +295,15 @@ class DecodeStepEngine:
         self.smem = lib.vg_decode_step_smem_bytes(NP)
         assert self.smem <= 227 * 1024, self.smem
         # ---- attention / barrier state
-        self.nsplit = max(1, min(16, G // (B * H)))
-        self.attn_partial = torch.zeros(B * H * self.nsplit * 66, dtype=torch.float32, device=device)
+        self.nsplit = attention_splits(B * H, G * 6)
+        self.attn_partial = torch.zeros(B * H * self.nsplit * 72, dtype=torch.float32, device=device)
         self.tickets = torch.zeros(B * H, dtype=torch.int32, device=device)
         self.bar_flags = torch.zeros(G + 128, dtype=torch.int32, device=device)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self.debug = torch.zeros(8, dtype=torch.int64, device=device)
         self.own_pos = torch.zeros(1, dtype=torch.int32, device=device)
         self.slopes = stack.rpe.slopes if stack.rpe is not None else None
-        self.barrier_mode = barrier_mode if barrier_mode >= 0 else int(os.environ.get("VG_DS_BARRIER", "2"))
+        self.barrier_mode = barrier_mode if barrier_mode >= 0 else int(os.environ.get("VG_DS_BARRIER", "1"))
         self.eps = eps
         self.trace = None                     # set to a [512] int64 device tensor to record per-phase barrier clocks
 
