@@ -346,7 +346,7 @@ int vg_zero_segments(float* base, const int64_t* seg_off, const int64_t* seg_len
  * lvtr.py:171,172,194,195) as ONE cooperative launch — stack-input linear, L x [RMSNorm1+QKV | cached attention + KV append |
  * out-proj+residual | RMSNorm3+FFN1 | GELU+FFN2+residual], final RMSNorm, q_spliter|token_spliter, prior/FiLM head, logits.
  * The step is a list of NP phases separated by device-wide barriers.  In a GEMM phase every CTA runs at most one unit of
- * the host-built task table `tasks[grid][NP]` (vae_gslm_b200/decode_step.py builds it): `R` (multiple of 8, <= 128) output
+ * the host-built task table `tasks[grid][NP]` (vae_gslm_b200/decode_step.py builds it): `R` (multiple of 16, <= 256) output
  * features x `nkb` 64-wide k-blocks of one linear layer as a swap-AB tcgen05 GEMM whose weight slab comes from the CTA's
  * own packed byte stream (`wstream + wstream_off[cta]`: per unit, per k-block, R/8 SWIZZLE_128B atoms of 8 rows x 64 bf16,
  * in consumption order) and whose X operand the CTA forms from `x` (x_kind 0: bf16 rows; 1: f32 rows * vec[k], optionally
@@ -384,7 +384,7 @@ typedef struct {
   int64_t cache_layer_stride, cache_kv_stride;          /* in elements */
   void* attn_out;                        /* bf16 [B, H*64] */
   const float* slopes;                   /* [H] ALiBi slopes (nullable) */
-  float* attn_partial;                   /* [B*H*nsplit*(64+2)] f32 (nsplit > 1) */
+  float* attn_partial;                   /* [B*H*nsplit*(64+8)] f32 (nsplit > 1) */
   int32_t* tickets;                      /* [B*H], zero on entry and left zero */
   int32_t* pos_dev;                      /* number of cached positions; advanced by the kernel when advance_pos */
   uint32_t* bar_flags; uint32_t* epoch;  /* barrier state, persistent across launches */
@@ -392,6 +392,7 @@ typedef struct {
   long long* trace;                      /* nullable: [grid][NP][8] clock64 stamps (barrier entry / exit, unit stages) */
   float inv_d, eps, scale;               /* 1/d_model, RMSNorm eps, softmax scale */
   int32_t NP, grid, B, Bp, H, Tmax, nsplit, barrier_mode, advance_pos;
+  int32_t attn_coop;                     /* 1: one CTA per attention item (few sequences); 0: one warp per item */
 } vg_decode_step_args;
 size_t vg_decode_step_task_bytes(void);
 size_t vg_decode_step_smem_bytes(int32_t n_phases);

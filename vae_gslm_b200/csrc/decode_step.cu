@@ -33,24 +33,24 @@ using namespace sm100;
 
 constexpr int DS_THREADS = 256;            // warp 0: weight producer, warp 1: MMA issuer, warps 2..7: workers (4..7: epilogue)
 constexpr int DS_WORKERS = 192;
-constexpr int DS_STAGE = 16384;            // weight ring stage
-constexpr int DS_NSTAGES = 8;
+constexpr int DS_STAGE = 32768;            // weight ring stage: one k-block slab of up to 256 features (or several smaller ones)
+constexpr int DS_NSTAGES = 4;
 constexpr int DS_XSLOT = 32768;            // X operand slot (two of them)
 constexpr int DS_HD = 64;                  // head dim
-constexpr int DS_GROUPS = (DS_WORKERS / 32) * 4;    // 24 key groups of 8 lanes
-constexpr int DS_KUNROLL = 4;
+constexpr int DS_AW = 7;                   // warps 1..7 take attention items (the MMA warp has nothing else to do there)
 constexpr long long DS_TIMEOUT = 4000000000LL;      // ~2 s of SM clocks
 
 typedef vg_decode_step_task DsTask;
 typedef vg_decode_step_args DsArgs;
 
 constexpr int DS_VEC_MAX = 1024;           // floats of a unit's per-k vector (RMSNorm scale / bias) prefetched into shared memory
-constexpr int DS_BIAS_MAX = 128;           // floats of a unit's output bias (R <= 128)
+constexpr int DS_BIAS_MAX = 256;           // floats of a unit's output bias (R <= 256)
 
 struct DsShared {
   uint64_t full[DS_NSTAGES], empty[DS_NSTAGES], xfull[2], xempty[2], accfull;
   uint32_t tmem_base;
-  int last[DS_WORKERS / 32];
+  float am[DS_AW], al[DS_AW];                // cooperative attention: per-warp partial softmax state of one item
+  __align__(16) float ao[DS_AW][DS_HD];
   float ss[256];
   int phase_kind[128];
   __align__(16) float vec[2][DS_VEC_MAX];
@@ -169,6 +169,9 @@ __device__ __forceinline__ void ds_prefetch_vec(const DsTask& t, DsShared& sh, i
 // Items of 8 consecutive k of one batch row; a thread loads DS_XU items before it touches any of them (the sources are
 // L2-resident accumulators: one dependent L2 round trip per item would be the whole cost of the transform).
 constexpr int DS_XU = 4;
+__device__ __forceinline__ float ds_act(float y, int act) {
+  return act == VG_ACT_GELU ? gelu_fast(y) : (act == VG_ACT_RELU ? fmaxf(y, 0.f) : y);
+}
 __device__ __forceinline__ void ds_transform(const DsArgs& a, const DsTask& t, DsShared& sh, uint8_t* xs, uint32_t& xcount,
                                              int par, int phase) {
   const int p = phase;
@@ -176,13 +179,15 @@ __device__ __forceinline__ void ds_transform(const DsArgs& a, const DsTask& t, D
   const int lane = threadIdx.x & 31;
   const int B = a.B, Bp = a.Bp;
   const int cap = DS_XSLOT / (Bp * 128);
-  const int xkb = t.nkb < cap ? t.nkb : cap;
+  const int xkb = t.nkb < cap ? t.nkb : cap;                   // a power of two (host contract)
   const int nchunks = t.nkb / xkb;
-  const int per_b = xkb * 8;
-  const int items = B * per_b;
+  const int lg = 31 - __clz(xkb * 8);                          // items (8 consecutive k of one row) per batch row = 1 << lg
+  const int per_b = 1 << lg;
+  const int items = B << lg;
   const int items_pad = (items + 31) & ~31;
   const bool want_ss = t.ss_out != nullptr;
   const bool vec_smem = ds_vec_prefetched(t);
+  const int kind = t.x_kind;
   if (wt < 64) ds_cp_async_wait_all();          // the prefetch of this unit's vectors (issued by these two warps)
   ds_named_bar(2, DS_WORKERS);
   for (int c = 0; c < nchunks; ++c) {
@@ -190,6 +195,7 @@ __device__ __forceinline__ void ds_transform(const DsArgs& a, const DsTask& t, D
     const uint32_t use = xcount >> 1;
     if (use > 0) ds_mbar_wait(&sh.xempty[slot], (use - 1) & 1, a, 10, phase);
     uint8_t* dst = xs + slot * DS_XSLOT;
+    const int kc0 = c * xkb * 64;                               // first k of this chunk relative to the unit's k0
     for (int base = wt; base < items_pad; base += DS_WORKERS * DS_XU) {
       uint4 raw0[DS_XU], raw1[DS_XU];
       float ssv[DS_XU];
@@ -198,32 +204,30 @@ __device__ __forceinline__ void ds_transform(const DsArgs& a, const DsTask& t, D
         const int item = base + u * DS_WORKERS;
         ssv[u] = 0.f;
         if (item < items) {
-          const int b = item / per_b;
-          const int rem = item - b * per_b;
-          const int k = t.k0 + (c * xkb + (rem >> 3)) * 64 + (rem & 7) * 8;
-          if (t.x_kind == 0) {
-            raw0[u] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t.x) + (size_t)b * t.ldx + k));
+          const int b = item >> lg;
+          const int kl = kc0 + ((item & (per_b - 1)) << 3);
+          if (kind == 0) {
+            raw0[u] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t.x) + (size_t)b * t.ldx +
+                                                            t.k0 + kl));
           } else {
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(t.x) + (size_t)b * t.ldx + k);
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(t.x) + (size_t)b * t.ldx + t.k0 + kl);
             raw0[u] = __ldcg(src);
             raw1[u] = __ldcg(src + 1);
-            if (t.x_kind == 2 && t.ss_in) ssv[u] = __ldcg(t.ss_in + b);
+            if (kind == 2 && t.ss_in) ssv[u] = __ldcg(t.ss_in + b);
           }
         }
       }
 #pragma unroll
       for (int u = 0; u < DS_XU; ++u) {
         const int item = base + u * DS_WORKERS;
-        if (item >= items_pad) break;             // warp-uniform: items_pad is a multiple of 32
         float ssq = 0.f;
-        int b = 0;
         if (item < items) {
-          b = item / per_b;
-          const int rem = item - b * per_b;
+          const int b = item >> lg;
+          const int rem = item & (per_b - 1);
           const int j = rem >> 3, g = rem & 7;
           uint4 packed = raw0[u];
-          if (t.x_kind != 0) {
-            const int kl = (c * xkb + j) * 64 + g * 8;                 // k relative to the unit's k0
+          if (kind != 0) {
+            const int kl = kc0 + (rem << 3);
             const float4* vp = vec_smem ? reinterpret_cast<const float4*>(&sh.vec[par][kl])
                                         : reinterpret_cast<const float4*>(t.vec + t.k0 + kl);
             const float4 s0 = vp[0], s1 = vp[1];
@@ -231,27 +235,32 @@ __device__ __forceinline__ void ds_transform(const DsArgs& a, const DsTask& t, D
                           __uint_as_float(raw0[u].w), __uint_as_float(raw1[u].x), __uint_as_float(raw1[u].y),
                           __uint_as_float(raw1[u].z), __uint_as_float(raw1[u].w)};
             const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            if (t.x_kind == 1) {
+            if (kind == 1) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) { ssq = fmaf(v[i], v[i], ssq); v[i] *= s[i]; }
             } else {
               const float rstd = t.ss_in ? rsqrtf(ssv[u] * t.inv_k + t.eps) : 1.0f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float y = fmaf(v[i], rstd, s[i]);
-                v[i] = t.act == VG_ACT_GELU ? gelu_fast(y) : (t.act == VG_ACT_RELU ? fmaxf(y, 0.f) : y);
-              }
+              for (int i = 0; i < 8; ++i) v[i] = ds_act(fmaf(v[i], rstd, s[i]), t.act);
             }
             packed.x = ds_pack_bf16(v[0], v[1]); packed.y = ds_pack_bf16(v[2], v[3]);
             packed.z = ds_pack_bf16(v[4], v[5]); packed.w = ds_pack_bf16(v[6], v[7]);
           }
           *reinterpret_cast<uint4*>(dst + j * (Bp * 128) + (b >> 3) * 1024 + (b & 7) * 128 + ((g ^ (b & 7)) << 4)) = packed;
         }
-        if (want_ss) {
-          // lanes of one batch row are contiguous: per_b (a power of two >= 8) lanes per row when per_b < 32, else whole warps
-          const int seg = per_b < 32 ? per_b : 32;
+        ssv[u] = ssq;
+      }
+      if (want_ss) {
+        // row sum-of-squares: lanes of one batch row are contiguous (per_b, a power of two >= 8, lanes per row when
+        // per_b < 32, else whole warps).  items_pad is a multiple of 32, so a warp is either wholly inside a round or out.
+        const int seg = per_b < 32 ? per_b : 32;
+#pragma unroll
+        for (int u = 0; u < DS_XU; ++u) {
+          const int item = base + u * DS_WORKERS;
+          if (item >= items_pad) break;
+          float ssq = ssv[u];
           for (int o = 1; o < seg; o <<= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
-          if ((lane & (seg - 1)) == 0 && item < items) atomicAdd(&sh.ss[b], ssq);
+          if ((lane & (seg - 1)) == 0 && item < items) atomicAdd(&sh.ss[item >> lg], ssq);
         }
       }
     }
@@ -301,14 +310,155 @@ __device__ __forceinline__ void ds_aux(const DsTask& t) {
   }
 }
 
-// ---- attention phase: items (b, h, split), ONE WARP per item (no CTA-level barriers inside the phase); 8 lanes share a
-// key row (16-byte loads: a warp instruction covers 4 full 128-byte rows), DS_KU x 4 keys of K and V in flight per warp,
-// online softmax per 8-lane group in the exp2 domain, groups merged with shuffles; with nsplit > 1 the last warp of a
-// (b, h) to arrive (ticket) merges the partials.  The new token's k / v come from the QKV sums of the phase before (· 1/rms,
-// rounded to bf16 — the value that goes into the cache) and are appended here.
-constexpr int DS_KU = 8;
+// ---- attention phase.  Items are (sequence, head, kv-split).  8 lanes share a key row (16-byte loads: a warp instruction
+// covers 4 full 128-byte rows); each warp keeps two sets of DS_KU x 4 keys of K and V in flight (the loads of the next
+// set are issued before the current one is consumed), online softmax per 8-lane group in the exp2 domain, the four groups
+// of a warp merged with shuffles.  Two ways to deal the items (host policy, a.attn_coop):
+//   0: one WARP per item — many (b, h): no CTA-level synchronisation inside the phase at all;
+//   1: one CTA per item, its seven attention warps take contiguous parts of the key range and merge through shared memory
+//      — few (b, h): short per-warp key ranges without a global ticket round trip.
+// With nsplit > 1 the last arriver of a (b, h) (ticket) merges the partials.  The new token's k / v come from the QKV sums
+// of the phase before (· 1/rms, rounded to bf16 — the value that goes into the cache) and are appended here.
+constexpr int DS_KU = 4;
+struct DsAttnState { float m, l, acc[8]; };
+
+__device__ __forceinline__ void ds_attn_load(uint4 (&kraw)[DS_KU], uint4 (&vraw)[DS_KU], int base, int j_end, int pos, int grp,
+                                             int sub, __nv_bfloat16* kc, __nv_bfloat16* vc, const float* row, int HD, float rstd) {
+#pragma unroll
+  for (int u = 0; u < DS_KU; ++u) {
+    const int j = base + u * 4 + grp;
+    if (j < j_end && j != pos) {
+      kraw[u] = __ldcs(reinterpret_cast<const uint4*>(kc + (size_t)j * DS_HD + sub * 8));
+      vraw[u] = __ldcs(reinterpret_cast<const uint4*>(vc + (size_t)j * DS_HD + sub * 8));
+    } else if (j == pos && j < j_end) {
+      const float4 k0 = __ldcg(reinterpret_cast<const float4*>(row + HD));
+      const float4 k1 = __ldcg(reinterpret_cast<const float4*>(row + HD) + 1);
+      const float4 v0 = __ldcg(reinterpret_cast<const float4*>(row + 2 * HD));
+      const float4 v1 = __ldcg(reinterpret_cast<const float4*>(row + 2 * HD) + 1);
+      kraw[u].x = ds_pack_bf16(k0.x * rstd, k0.y * rstd); kraw[u].y = ds_pack_bf16(k0.z * rstd, k0.w * rstd);
+      kraw[u].z = ds_pack_bf16(k1.x * rstd, k1.y * rstd); kraw[u].w = ds_pack_bf16(k1.z * rstd, k1.w * rstd);
+      vraw[u].x = ds_pack_bf16(v0.x * rstd, v0.y * rstd); vraw[u].y = ds_pack_bf16(v0.z * rstd, v0.w * rstd);
+      vraw[u].z = ds_pack_bf16(v1.x * rstd, v1.y * rstd); vraw[u].w = ds_pack_bf16(v1.z * rstd, v1.w * rstd);
+      *reinterpret_cast<uint4*>(kc + (size_t)pos * DS_HD + sub * 8) = kraw[u];
+      *reinterpret_cast<uint4*>(vc + (size_t)pos * DS_HD + sub * 8) = vraw[u];
+    } else {
+      kraw[u] = make_uint4(0, 0, 0, 0);
+      vraw[u] = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+__device__ __forceinline__ void ds_attn_consume(DsAttnState& st, const uint4 (&kraw)[DS_KU], const uint4 (&vraw)[DS_KU], int base,
+                                                int j_end, int pos, int grp, const float (&q)[8], float slope) {
+#pragma unroll
+  for (int u = 0; u < DS_KU; ++u) {
+    const int j = base + u * 4 + grp;
+    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kraw[u]);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(k2[i]);
+      s = fmaf(q[2 * i], f.x, s);
+      s = fmaf(q[2 * i + 1], f.y, s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (j < j_end) {
+      s -= slope * (float)(pos - j);
+      const float mnew = fmaxf(st.m, s);
+      const float corr = ex2_approx(st.m - mnew);           // m = -inf on the first key → 0
+      const float pr = ex2_approx(s - mnew);
+      st.l = st.l * corr + pr;
+      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vraw[u]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(v2[i]);
+        st.acc[2 * i] = fmaf(pr, f.x, st.acc[2 * i] * corr);
+        st.acc[2 * i + 1] = fmaf(pr, f.y, st.acc[2 * i + 1] * corr);
+      }
+      st.m = mnew;
+    }
+  }
+}
+// keys [j0, j1) of one (b, h) by one warp; on return lanes 0..7 (grp 0) hold the warp's (m, l, acc) for dims sub*8..sub*8+7
+__device__ __forceinline__ void ds_attn_range(DsAttnState& st, int j0, int j1, int pos, int grp, int sub, __nv_bfloat16* kc,
+                                              __nv_bfloat16* vc, const float* row, int HD, float rstd, const float (&q)[8],
+                                              float slope) {
+  st.m = -CUDART_INF_F; st.l = 0.f;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) st.acc[d] = 0.f;
+  uint4 ka[DS_KU], va[DS_KU], kb[DS_KU], vb[DS_KU];
+  if (j0 < j1) ds_attn_load(ka, va, j0, j1, pos, grp, sub, kc, vc, row, HD, rstd);
+  for (int base = j0; base < j1; base += 8 * DS_KU) {
+    const int b1 = base + 4 * DS_KU, b2 = base + 8 * DS_KU;
+    if (b1 < j1) ds_attn_load(kb, vb, b1, j1, pos, grp, sub, kc, vc, row, HD, rstd);
+    ds_attn_consume(st, ka, va, base, j1, pos, grp, q, slope);
+    if (b2 < j1) ds_attn_load(ka, va, b2, j1, pos, grp, sub, kc, vc, row, HD, rstd);
+    if (b1 < j1) ds_attn_consume(st, kb, vb, b1, j1, pos, grp, q, slope);
+  }
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, st.m, off);
+    const float lo = __shfl_xor_sync(0xffffffffu, st.l, off);
+    const float mn = fmaxf(st.m, mo);
+    const float wa = (st.m == -CUDART_INF_F) ? 0.f : ex2_approx(st.m - mn);
+    const float wb = (mo == -CUDART_INF_F) ? 0.f : ex2_approx(mo - mn);
+    st.l = st.l * wa + lo * wb;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) st.acc[d] = st.acc[d] * wa + __shfl_xor_sync(0xffffffffu, st.acc[d], off) * wb;
+    st.m = mn;
+  }
+}
+// one warp publishes (m, l, o[64]) of (b, h, split) — lanes 0..7 hold it — and, if it is the last split to arrive, merges
+__device__ __forceinline__ void ds_attn_finish(const DsArgs& a, const DsAttnState& st, int bh, int split, int b, int h, int lane) {
+  const int HD = a.H * DS_HD, nsplit = a.nsplit;
+  const int grp = lane >> 3, sub = lane & 7;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.attn_out);
+  if (nsplit == 1) {
+    if (grp == 0) {
+      const float inv = st.l > 0.f ? 1.0f / st.l : 0.f;
+      uint4 o;
+      o.x = ds_pack_bf16(st.acc[0] * inv, st.acc[1] * inv); o.y = ds_pack_bf16(st.acc[2] * inv, st.acc[3] * inv);
+      o.z = ds_pack_bf16(st.acc[4] * inv, st.acc[5] * inv); o.w = ds_pack_bf16(st.acc[6] * inv, st.acc[7] * inv);
+      *reinterpret_cast<uint4*>(out + (size_t)b * HD + h * DS_HD + sub * 8) = o;
+    }
+    return;
+  }
+  float* pp = a.attn_partial + ((size_t)bh * nsplit + split) * (DS_HD + 8);      // [m, l, pad.., o[64]], 16-byte aligned rows
+  if (grp == 0) {
+    __stcg(reinterpret_cast<float4*>(pp + 8 + sub * 8), make_float4(st.acc[0], st.acc[1], st.acc[2], st.acc[3]));
+    __stcg(reinterpret_cast<float4*>(pp + 8 + sub * 8) + 1, make_float4(st.acc[4], st.acc[5], st.acc[6], st.acc[7]));
+    if (sub == 0) __stcg(reinterpret_cast<float2*>(pp), make_float2(st.m, st.l));
+  }
+  // ticket: zero on entry and left zero.  __syncwarp orders the eight writers before lane 0's release.
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(a.tickets + bh) : "memory");
+    last = (old == nsplit - 1);
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  const float* p0 = a.attn_partial + (size_t)bh * nsplit * (DS_HD + 8);
+  float M2 = -CUDART_INF_F;
+  for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, __ldcg(p0 + s2 * (DS_HD + 8)));
+  float L2 = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int s2 = 0; s2 < nsplit; ++s2) {
+    const float2 ml = __ldcg(reinterpret_cast<const float2*>(p0 + s2 * (DS_HD + 8)));
+    const float w = (ml.x == -CUDART_INF_F) ? 0.f : ex2_approx(ml.x - M2);
+    const float2 ov = __ldcg(reinterpret_cast<const float2*>(p0 + s2 * (DS_HD + 8) + 8 + lane * 2));
+    L2 = fmaf(ml.y, w, L2);
+    o0 = fmaf(ov.x, w, o0);
+    o1 = fmaf(ov.y, w, o1);
+  }
+  const float inv = L2 > 0.f ? 1.0f / L2 : 0.f;
+  *reinterpret_cast<uint32_t*>(out + (size_t)b * HD + h * DS_HD + lane * 2) = ds_pack_bf16(o0 * inv, o1 * inv);
+  if (lane == 0) a.tickets[bh] = 0;
+}
+
 __device__ __forceinline__ void ds_attention(const DsArgs& a, DsShared& sh, int layer, int pos, int phase) {
-  const int ww = (threadIdx.x >> 5) - 2;        // 0..5
+  const int aw = (threadIdx.x >> 5) - 1;        // 0..6 (warps 1..7)
   const int lane = threadIdx.x & 31;
   const int grp = lane >> 3, sub = lane & 7;
   const int H = a.H, HD = a.H * DS_HD;
@@ -317,9 +467,10 @@ __device__ __forceinline__ void ds_attention(const DsArgs& a, DsShared& sh, int 
   const int nkeys = pos + 1;
   const int chunk = (nkeys + nsplit - 1) / nsplit;
   const float* ss = a.ss_base + (size_t)(2 * layer) * a.B;
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.attn_out);
   constexpr float LOG2E = 1.4426950408889634f;
-  for (int item = blockIdx.x * (DS_WORKERS / 32) + ww; item < n_items; item += gridDim.x * (DS_WORKERS / 32)) {
+  const int first = a.attn_coop ? (int)blockIdx.x : (int)blockIdx.x * DS_AW + aw;
+  const int stride = a.attn_coop ? (int)gridDim.x : (int)gridDim.x * DS_AW;
+  for (int item = first; item < n_items; item += stride) {
     const int split = item % nsplit;
     const int bh = item / nsplit;
     const int h = bh % H, b = bh / H;
@@ -339,116 +490,39 @@ __device__ __forceinline__ void ds_attention(const DsArgs& a, DsShared& sh, int 
     __nv_bfloat16* vc = kc + a.cache_kv_stride;
     const int j_begin = split * chunk;
     const int j_end = min(nkeys, j_begin + chunk);
-    float m = -CUDART_INF_F, l = 0.f, acc[8];
-#pragma unroll
-    for (int d = 0; d < 8; ++d) acc[d] = 0.f;
-    for (int base = j_begin; base < j_end; base += 4 * DS_KU) {
-      uint4 kraw[DS_KU], vraw[DS_KU];
-#pragma unroll
-      for (int u = 0; u < DS_KU; ++u) {
-        const int j = base + u * 4 + grp;
-        if (j < j_end && j != pos) {
-          kraw[u] = __ldcs(reinterpret_cast<const uint4*>(kc + (size_t)j * DS_HD + sub * 8));
-          vraw[u] = __ldcs(reinterpret_cast<const uint4*>(vc + (size_t)j * DS_HD + sub * 8));
-        } else if (j == pos && j < j_end) {
-          const float4 k0 = __ldcg(reinterpret_cast<const float4*>(row + HD));
-          const float4 k1 = __ldcg(reinterpret_cast<const float4*>(row + HD) + 1);
-          const float4 v0 = __ldcg(reinterpret_cast<const float4*>(row + 2 * HD));
-          const float4 v1 = __ldcg(reinterpret_cast<const float4*>(row + 2 * HD) + 1);
-          kraw[u].x = ds_pack_bf16(k0.x * rstd, k0.y * rstd); kraw[u].y = ds_pack_bf16(k0.z * rstd, k0.w * rstd);
-          kraw[u].z = ds_pack_bf16(k1.x * rstd, k1.y * rstd); kraw[u].w = ds_pack_bf16(k1.z * rstd, k1.w * rstd);
-          vraw[u].x = ds_pack_bf16(v0.x * rstd, v0.y * rstd); vraw[u].y = ds_pack_bf16(v0.z * rstd, v0.w * rstd);
-          vraw[u].z = ds_pack_bf16(v1.x * rstd, v1.y * rstd); vraw[u].w = ds_pack_bf16(v1.z * rstd, v1.w * rstd);
-          *reinterpret_cast<uint4*>(kc + (size_t)pos * DS_HD + sub * 8) = kraw[u];
-          *reinterpret_cast<uint4*>(vc + (size_t)pos * DS_HD + sub * 8) = vraw[u];
-        } else {
-          kraw[u] = make_uint4(0, 0, 0, 0);
-          vraw[u] = make_uint4(0, 0, 0, 0);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < DS_KU; ++u) {
-        const int j = base + u * 4 + grp;
-        const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kraw[u]);
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(k2[i]);
-          s = fmaf(q[2 * i], f.x, s);
-          s = fmaf(q[2 * i + 1], f.y, s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (j < j_end) {
-          s -= slope * (float)(pos - j);
-          const float mnew = fmaxf(m, s);
-          const float corr = ex2_approx(m - mnew);           // m = -inf on the first key → 0
-          const float pr = ex2_approx(s - mnew);
-          l = l * corr + pr;
-          const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vraw[u]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(v2[i]);
-            acc[2 * i] = fmaf(pr, f.x, acc[2 * i] * corr);
-            acc[2 * i + 1] = fmaf(pr, f.y, acc[2 * i + 1] * corr);
-          }
-          m = mnew;
-        }
-      }
-    }
-    // merge the four 8-lane groups (same sub = same head dims): lanes 0..7 end up with the warp's result
-#pragma unroll
-    for (int off = 8; off <= 16; off <<= 1) {
-      const float mo = __shfl_xor_sync(0xffffffffu, m, off);
-      const float lo = __shfl_xor_sync(0xffffffffu, l, off);
-      const float mn = fmaxf(m, mo);
-      const float wa = (m == -CUDART_INF_F) ? 0.f : ex2_approx(m - mn);
-      const float wb = (mo == -CUDART_INF_F) ? 0.f : ex2_approx(mo - mn);
-      l = l * wa + lo * wb;
-#pragma unroll
-      for (int d = 0; d < 8; ++d) acc[d] = acc[d] * wa + __shfl_xor_sync(0xffffffffu, acc[d], off) * wb;
-      m = mn;
-    }
-    if (nsplit == 1) {
-      if (grp == 0) {
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
-        uint4 o;
-        o.x = ds_pack_bf16(acc[0] * inv, acc[1] * inv); o.y = ds_pack_bf16(acc[2] * inv, acc[3] * inv);
-        o.z = ds_pack_bf16(acc[4] * inv, acc[5] * inv); o.w = ds_pack_bf16(acc[6] * inv, acc[7] * inv);
-        *reinterpret_cast<uint4*>(out + (size_t)b * HD + h * DS_HD + sub * 8) = o;
-      }
+    DsAttnState st;
+    if (!a.attn_coop) {
+      ds_attn_range(st, j_begin, j_end, pos, grp, sub, kc, vc, row, HD, rstd, q, slope);
+      ds_attn_finish(a, st, bh, split, b, h, lane);
     } else {
-      float* pp = a.attn_partial + ((size_t)bh * nsplit + split) * (DS_HD + 8);      // [m, l, pad.., o[64]] 16-byte aligned rows
+      // the seven warps of this CTA split [j_begin, j_end) into contiguous parts (multiples of 4 keys)
+      const int len = max(0, j_end - j_begin);
+      const int part = ((len + DS_AW - 1) / DS_AW + 3) & ~3;
+      const int j0 = min(j_end, j_begin + aw * part), j1 = min(j_end, j0 + part);
+      ds_attn_range(st, j0, j1, pos, grp, sub, kc, vc, row, HD, rstd, q, slope);
       if (grp == 0) {
-        __stcg(reinterpret_cast<float4*>(pp + 8 + sub * 8), make_float4(acc[0], acc[1], acc[2], acc[3]));
-        __stcg(reinterpret_cast<float4*>(pp + 8 + sub * 8) + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
-        if (sub == 0) __stcg(reinterpret_cast<float2*>(pp), make_float2(m, l));
+        if (sub == 0) { sh.am[aw] = st.m; sh.al[aw] = st.l; }
+        *reinterpret_cast<float4*>(&sh.ao[aw][sub * 8]) = make_float4(st.acc[0], st.acc[1], st.acc[2], st.acc[3]);
+        *reinterpret_cast<float4*>(&sh.ao[aw][sub * 8 + 4]) = make_float4(st.acc[4], st.acc[5], st.acc[6], st.acc[7]);
       }
-      // the last split of (b, h) to arrive merges (tickets are zero on entry and left zero)
-      __threadfence();
-      __syncwarp();
-      int last = 0;
-      if (lane == 0) last = (atomicAdd(a.tickets + bh, 1) == nsplit - 1);
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {
-        __threadfence();
-        const float* p0 = a.attn_partial + (size_t)bh * nsplit * (DS_HD + 8);
-        float M2 = -CUDART_INF_F;
-        for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, __ldcg(p0 + s2 * (DS_HD + 8)));
-        float L2 = 0.f, o0 = 0.f, o1 = 0.f;
-        for (int s2 = 0; s2 < nsplit; ++s2) {
-          const float2 ml = __ldcg(reinterpret_cast<const float2*>(p0 + s2 * (DS_HD + 8)));
-          const float w = (ml.x == -CUDART_INF_F) ? 0.f : ex2_approx(ml.x - M2);
-          const float2 ov = __ldcg(reinterpret_cast<const float2*>(p0 + s2 * (DS_HD + 8) + 8 + lane * 2));
-          L2 = fmaf(ml.y, w, L2);
-          o0 = fmaf(ov.x, w, o0);
-          o1 = fmaf(ov.y, w, o1);
+      ds_named_bar(3, DS_AW * 32);
+      if (aw == 0) {
+        float M = -CUDART_INF_F;
+#pragma unroll
+        for (int w = 0; w < DS_AW; ++w) M = fmaxf(M, sh.am[w]);
+        st.m = M; st.l = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) st.acc[d] = 0.f;
+#pragma unroll
+        for (int w = 0; w < DS_AW; ++w) {
+          const float wgt = (sh.am[w] == -CUDART_INF_F) ? 0.f : ex2_approx(sh.am[w] - M);
+          st.l = fmaf(sh.al[w], wgt, st.l);
+#pragma unroll
+          for (int d = 0; d < 8; ++d) st.acc[d] = fmaf(sh.ao[w][sub * 8 + d], wgt, st.acc[d]);
         }
-        const float inv = L2 > 0.f ? 1.0f / L2 : 0.f;
-        *reinterpret_cast<uint32_t*>(out + (size_t)b * HD + h * DS_HD + lane * 2) = ds_pack_bf16(o0 * inv, o1 * inv);
-        if (lane == 0) a.tickets[bh] = 0;
+        ds_attn_finish(a, st, bh, split, b, h, lane);
       }
+      ds_named_bar(3, DS_AW * 32);             // sh.am / al / ao are reused by the next item
     }
   }
 }
@@ -531,7 +605,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
       const DsTask& t = tasks[p];
       const int kind = sh.phase_kind[p];
       if (kind >= 0) {
-        if (warp >= 2) ds_attention(a, sh, kind, pos, p);
+        ds_attention(a, sh, kind, pos, p);            // warps 1..7
       } else if (t.R > 0) {
         const int xkb = t.nkb < cap ? t.nkb : cap;
         const int par = ntask & 1;
@@ -580,25 +654,42 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
               tc_fence_after();
               DS_TRACE(4, 128);
               for (int mt = 0; mt < mtiles; ++mt) {
-                const int b = mt * 128 + q * 32 + lane;
                 if (mt * 128 + q * 32 >= a.B) break;
-                float* orow = t.acc + (size_t)b * t.ldacc + t.n0;
-                for (int c0 = 0; c0 < t.rows; c0 += 16) {
-                  uint32_t v[16];
-                  tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * t.R + c0), v);
+                const bool vec4 = (t.ldacc & 3) == 0;            // 16-byte vector atomics need 16-byte aligned rows
+                // 32 columns at a time: thread = batch row (TMEM lane) holds 32 consecutive features.  One lane per row
+                // issuing the atomics is slow when few rows are valid (batch 1: 48 dependent 16-byte atomics from ONE
+                // lane cost 8.8 k cycles), so the chunk goes through a warp-private, XOR-swizzled 4 KB staging tile and
+                // comes back as (row, 4 features) per lane: 8 consecutive lanes cover 128 contiguous bytes of one row.
+                float4* stg = reinterpret_cast<float4*>(xs) + q * 256;      // X slots are idle once the accumulator is complete
+                const int rows_here = min(32, a.B - (mt * 128 + q * 32));
+                for (int c0 = 0; c0 < t.rows; c0 += 32) {
+                  uint32_t v[32];
+                  tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * t.R + c0), v);
                   tmem_ld_wait();
-                  if (b < a.B) {
+                  __syncwarp();
+                  if (lane < rows_here) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                      if (c0 + 4 * g < t.rows) {            // rows is a multiple of 4
-                        float4 val = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                                 __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-                        if (t.bias_out) {
-                          const float4 bb = *reinterpret_cast<const float4*>(&sh.bias[par][c0 + 4 * g]);
-                          val.x += bb.x; val.y += bb.y; val.z += bb.z; val.w += bb.w;
-                        }
-                        if (t.store) __stcg(reinterpret_cast<float4*>(orow + c0 + 4 * g), val);
-                        else ds_red_add4(orow + c0 + 4 * g, val.x, val.y, val.z, val.w);
+                    for (int g = 0; g < 8; ++g)
+                      stg[lane * 8 + (g ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                                                    __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+                  }
+                  __syncwarp();
+                  const int g = lane & 7;
+                  if (c0 + 4 * g < t.rows) {                    // rows is a multiple of 4
+                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t.bias_out) bb = *reinterpret_cast<const float4*>(&sh.bias[par][c0 + 4 * g]);
+                    for (int r = lane >> 3; r < rows_here; r += 4) {
+                      float4 val = stg[r * 8 + (g ^ (r & 7))];
+                      val.x += bb.x; val.y += bb.y; val.z += bb.z; val.w += bb.w;
+                      float* dst = t.acc + (size_t)(mt * 128 + q * 32 + r) * t.ldacc + t.n0 + c0 + 4 * g;
+                      if (!vec4) {
+                        const float e[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { if (t.store) __stcg(dst + i, e[i]); else ds_red_add(dst + i, e[i]); }
+                      } else if (t.store) {
+                        __stcg(reinterpret_cast<float4*>(dst), val);
+                      } else {
+                        ds_red_add4(dst, val.x, val.y, val.z, val.w);
                       }
                     }
                   }

@@ -43,17 +43,17 @@ def _rows_per_unit(N: int, S: int, units: int = UNITS) -> int:
     return max(16, (-(-(N * S) // units) + 15) // 16 * 16)
 
 
-def split_factor(N: int, K: int, units: int = UNITS, max_split: int = 16) -> Tuple[int, int]:
-    """(R, S) for a [N, K] linear: the LARGEST k-split S (power of two) whose units still have R <= 128 output features.
-    A unit always costs a full 128-row tcgen05 tile per 16-wide k step (the slab is the M operand whatever R is), so the
-    MMA time of a phase is proportional to the k-blocks per unit: wide-and-short units (R = 128, few k-blocks) are the fast
-    shape at EVERY batch size, they also keep the X operand of a CTA small; the price is S partial sums per output,
-    reduced with red.global.add.f32 into the fp32 accumulators (measured: far below a barrier, profiles/r02_microbench.md)."""
+def split_factor(N: int, K: int, units: int = UNITS, max_split: int = 32, rmax: int = 128) -> Tuple[int, int]:
+    """(R, S) for a [N, K] linear: the LARGEST k-split S (power of two) whose units still have R <= rmax output features.
+    A tcgen05.mma of this kernel costs ~180 cycles whatever its N (measured, profiles/r02_decode.md), so the MMA time of a
+    phase is proportional to the k-blocks per unit: wide-and-short units are the fast shape at EVERY batch size, and they
+    keep the X operand a CTA must form small; the price is S partial sums per output, reduced with
+    red.global.add.v4.f32 into the fp32 accumulators — which is why rmax is 256 only for small batches."""
     best = None
     S = 1
     while S <= max_split:
         R = _rows_per_unit(N, S, units)
-        if R > 128 or (K // 64) % S or K // 64 // S < 1:
+        if R > rmax or (K // 64) % S or K // 64 // S < 1:
             break
         best = (R, S)
         S *= 2
@@ -84,7 +84,7 @@ def attention_splits(n_bh: int, n_warps: int) -> int:
     """kv-splits per (sequence, head) for the attention phases: items = n_bh * splits are dealt round-robin to the
     ``n_warps`` worker warps of the grid (one warp per item).  Few (b, h): about half a wave of short items (the merge of
     the partials by the last arriver grows with the split count); many: the smallest split whose last wave is >= 85 % full."""
-    if n_bh * 2 <= n_warps:
+    if n_bh * 4 <= n_warps:
         return max(1, min(64, n_warps // (2 * n_bh)))
     for s in (1, 2, 4, 8, 16):
         items = n_bh * s
@@ -103,6 +103,7 @@ class _Args(C.Structure):
         ("inv_d", C.c_float), ("eps", C.c_float), ("scale", C.c_float),
         ("NP", C.c_int32), ("grid", C.c_int32), ("B", C.c_int32), ("Bp", C.c_int32), ("H", C.c_int32),
         ("Tmax", C.c_int32), ("nsplit", C.c_int32), ("barrier_mode", C.c_int32), ("advance_pos", C.c_int32),
+        ("attn_coop", C.c_int32),
     ]
 
 
@@ -177,6 +178,7 @@ class DecodeStepEngine:
             keep.append(t)
             return t.data_ptr()
 
+        rmax = 256 if B <= 32 else 128          # output features per unit (= the N of the MMA): see split_factor
         # ---- phases
         rs_log: List[Tuple[int, int]] = []
         phases = []          # each: dict(kind=-1|layer, units=[...], aux=None|...)
@@ -184,10 +186,10 @@ class DecodeStepEngine:
         inv_d = 1.0 / d
 
         def gemm_units(W, B_, x_ptr, ldx, x_kind, acc_ptr, ldacc, *, vec_ptr=0, act=ACT_NONE, ss_in=0, ss_out=0,
-                       bias_out=0, store=0, inv_k=inv_d, n_off=0, max_split=16, units=UNITS):
+                       bias_out=0, store=0, inv_k=inv_d, n_off=0, max_split=32, units=UNITS):
             """units of one linear layer W [N, K] → list of (task dict, packed slab tensor)"""
             N, K = W.shape
-            R, S = split_factor(N, K, units=units, max_split=1 if store else max_split)
+            R, S = split_factor(N, K, units=units, max_split=1 if store else max_split, rmax=rmax)
             packed = pack_units(W.detach().to(bf), R, S)
             rs_log.append((R, S))
             n_slabs, nkb = packed.shape[0], K // 64 // S
@@ -213,21 +215,20 @@ class DecodeStepEngine:
             sa = lyr.self_attn
             phases.append(dict(kind=-1, name=f"qkv{i}", aux=zero_job("f1", B * ffd), units=gemm_units(
                 sa.in_proj.weight, B, self.h.data_ptr(), d, 1, self.qkv_acc.data_ptr(), 3 * d, vec_ptr=vec(lyr.norm1.scale),
-                ss_out=ss_ptr(2 * i), max_split=4)))
+                ss_out=ss_ptr(2 * i))))
             phases.append(dict(kind=i, name=f"attn{i}", aux=None, units=[]))
             phases.append(dict(kind=-1, name=f"out{i}", aux=zero_job("qkv", B * 3 * d), units=gemm_units(
                 sa.out_proj.weight, B, self.o.data_ptr(), d, 0, self.h.data_ptr(), d)))
             phases.append(dict(kind=-1, name=f"ffn1_{i}", aux=None, units=gemm_units(
                 lyr.linear1.weight, B, self.h.data_ptr(), d, 1, self.f1_acc.data_ptr(), ffd, vec_ptr=vec(lyr.norm3.scale),
-                ss_out=ss_ptr(2 * i + 1), max_split=4)))
+                ss_out=ss_ptr(2 * i + 1))))
             b1 = lyr.linear1.bias if lyr.linear1.bias is not None else torch.zeros(ffd, device=device)
             phases.append(dict(kind=-1, name=f"ffn2_{i}", aux=None, units=gemm_units(
                 lyr.linear2.weight, B, self.f1_acc.data_ptr(), ffd, 2, self.h.data_ptr(), d, vec_ptr=vec(b1), act=ACT_GELU,
                 ss_in=ss_ptr(2 * i + 1), bias_out=vec(lyr.linear2.bias) if lyr.linear2.bias is not None else 0)))
         fn = vec(stack.final_norm.scale)
         phases.append(dict(kind=-1, name="split", aux=None, units=gemm_units(
-            w_split, B, self.h.data_ptr(), d, 1, self.cg_acc.data_ptr(), 2 * d, vec_ptr=fn, ss_out=ss_ptr(2 * Lr),
-            max_split=8)))
+            w_split, B, self.h.data_ptr(), d, 1, self.cg_acc.data_ptr(), 2 * d, vec_ptr=fn, ss_out=ss_ptr(2 * Lr))))
         bs = f32(b_split)
         keep.append(bs)
         head_units = gemm_units(w_head, B, self.cg_acc.data_ptr(), 2 * d, 2, self.head.data_ptr(), n_head,
@@ -295,7 +296,9 @@ class DecodeStepEngine:
         self.smem = lib.vg_decode_step_smem_bytes(NP)
         assert self.smem <= 227 * 1024, self.smem
         # ---- attention / barrier state
-        self.nsplit = attention_splits(B * H, G * 6)
+        # attention: few (sequence, head) pairs → one CTA per (pair, split), up to 4 kv-splits; many → one warp per (pair, split)
+        self.attn_coop = 1 if B * H <= G else 0
+        self.nsplit = max(1, min(4, G // (B * H))) if self.attn_coop else attention_splits(B * H, G * 7)
         self.attn_partial = torch.zeros(B * H * self.nsplit * 72, dtype=torch.float32, device=device)
         self.tickets = torch.zeros(B * H, dtype=torch.int32, device=device)
         self.bar_flags = torch.zeros(G + 128, dtype=torch.int32, device=device)
@@ -325,6 +328,7 @@ class DecodeStepEngine:
         a.inv_d, a.eps, a.scale = 1.0 / self.dim, self.eps, 1.0 / 8.0
         a.NP, a.grid, a.B, a.Bp, a.H = self.NP, self.grid, self.batch, self.Bp, self.nheads
         a.Tmax, a.nsplit, a.barrier_mode, a.advance_pos = cache.max_len, self.nsplit, self.barrier_mode, advance
+        a.attn_coop = self.attn_coop
         return a
 
     @torch.no_grad()
