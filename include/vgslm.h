@@ -392,6 +392,7 @@ typedef struct {
   long long* trace;                      /* nullable: [grid][NP][8] clock64 stamps (barrier entry / exit, unit stages) */
   float inv_d, eps, scale;               /* 1/d_model, RMSNorm eps, softmax scale */
   int32_t NP, grid, B, Bp, H, Tmax, nsplit, barrier_mode, advance_pos;
+  int32_t rep;                           /* copies of the batch rows in the X tile / accumulator: 4 (B <= 32), 2 (<= 64), 1 */
   int32_t attn_coop;                     /* 1: one CTA per attention item (few sequences); 0: one warp per item */
 } vg_decode_step_args;
 size_t vg_decode_step_task_bytes(void);

@@ -44,14 +44,14 @@ work = tr[:, 1:NP - 1, 0] - tr[:, 0:NP - 2, 1]          # [G, phases 1..NP-2]
 wait = tr[:, 1:NP - 1, 1] - tr[:, 1:NP - 1, 0]
 names = [n.rstrip("0123456789").rstrip("_") for n in eng.phase_names[1:NP - 1]]
 print(f"total (CTA 0, first to last barrier exit): {int(tr[0, NP - 2, 1] - tr[0, 0, 1])} cycles")
-print(f"{'phase':6s} {'n':>3s} {'work mean':>10s} {'work max':>10s} {'wait min':>10s} {'phase len':>10s} | slowest CTA: X published, W+X ready (mma warp), first k-block issued, all issued, acc ready, epilogue done (cycles after barrier exit)")
+print(f"{'phase':6s} {'n':>3s} {'work mean':>10s} {'work max':>10s} {'wait min':>10s} {'phase len':>10s} | slowest CTA: X published, all mma issued, acc ready, first tmem read, first chunk reduced, epilogue done (cycles after barrier exit)")
 for k in dict.fromkeys(names):
     idx = [i for i, n in enumerate(names) if n == k]
     w, wt = work[:, idx], wait[:, idx]
     plen = (w + wt).mean()
     slow = w.argmax(0)                                  # slowest CTA per phase instance
     st = []
-    for slot in (7, 6, 2, 3, 4, 5):
+    for slot in (7, 3, 4, 6, 2, 5):
         vals = [float(tr[int(slow[j]), idx[j] + 1, slot] - tr[int(slow[j]), idx[j], 1]) for j in range(len(idx))]
         st.append(sum(vals) / len(vals))
     print(f"{k:6s} {len(idx):3d} {float(w.mean()):10.0f} {float(w.max(0).values.mean()):10.0f} {float(wt.min(0).values.mean()):10.0f} "

@@ -246,7 +246,11 @@ __device__ __forceinline__ void ds_transform(const DsArgs& a, const DsTask& t, D
             packed.x = ds_pack_bf16(v[0], v[1]); packed.y = ds_pack_bf16(v[2], v[3]);
             packed.z = ds_pack_bf16(v[4], v[5]); packed.w = ds_pack_bf16(v[6], v[7]);
           }
-          *reinterpret_cast<uint4*>(dst + j * (Bp * 128) + (b >> 3) * 1024 + (b & 7) * 128 + ((g ^ (b & 7)) << 4)) = packed;
+          // a.rep copies of the row, 128 / a.rep rows apart: every TMEM lane quadrant then holds the batch (see the epilogue)
+          for (int r = 0; r < a.rep; ++r) {
+            const int br = b + r * (128 / a.rep);
+            *reinterpret_cast<uint4*>(dst + j * (Bp * 128) + (br >> 3) * 1024 + (br & 7) * 128 + ((g ^ (br & 7)) << 4)) = packed;
+          }
         }
         ssv[u] = ssq;
       }
@@ -622,7 +626,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
             const int slot = xcount & 1;
             if (jw == 0) ds_mbar_wait(&sh.full[s], (wcount / DS_NSTAGES) & 1, a, 2, p);
             if (jx == 0) ds_mbar_wait(&sh.xfull[slot], (xcount >> 1) & 1, a, 3, p);
-            if (j == 0) DS_TRACE(6, 32);
             tc_fence_after();
             const uint32_t w_addr = smem_u32(ring + s * DS_STAGE + jw * slab);
             const uint32_t x_addr = smem_u32(xs + slot * DS_XSLOT + jx * (a.Bp * 128));
@@ -639,7 +642,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
               if (j == t.nkb - 1) umma_commit(&sh.accfull);
             }
             __syncwarp();
-            if (j == 0) DS_TRACE(2, 32);
             if (w_done) ++wcount;
             if (x_done) ++xcount;
           }
@@ -649,20 +651,26 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
           ds_transform(a, t, sh, xs, xcount, par, p);
           if (warp >= 4) {
             const int q = warp - 4;
-            if (q * 32 < a.B) {
+            // With a.rep copies of the batch in the accumulator (rows b + i * 128 / rep), quadrant q reads copy
+            // q / (4 / rep) and takes every rep-th 32-column chunk: at batch <= 32 all four epilogue warps work on
+            // different columns of the same rows instead of one warp doing everything.
+            const int qper = 4 / a.rep;                         // quadrants per copy
+            const int copy = q / qper, qrow = (q % qper) * 32;  // first batch row of this warp within its copy
+            if (qrow < a.B || mtiles == 2) {
               ds_mbar_wait(&sh.accfull, ntask & 1, a, 4, p);
               tc_fence_after();
               DS_TRACE(4, 128);
               for (int mt = 0; mt < mtiles; ++mt) {
-                if (mt * 128 + q * 32 >= a.B) break;
+                const int row0 = mt * 128 + qrow;
+                if (row0 >= a.B) break;
                 const bool vec4 = (t.ldacc & 3) == 0;            // 16-byte vector atomics need 16-byte aligned rows
                 // 32 columns at a time: thread = batch row (TMEM lane) holds 32 consecutive features.  One lane per row
-                // issuing the atomics is slow when few rows are valid (batch 1: 48 dependent 16-byte atomics from ONE
-                // lane cost 8.8 k cycles), so the chunk goes through a warp-private, XOR-swizzled 4 KB staging tile and
-                // comes back as (row, 4 features) per lane: 8 consecutive lanes cover 128 contiguous bytes of one row.
+                // issuing the atomics is slow when few rows are valid, so the chunk goes through a warp-private,
+                // XOR-swizzled 4 KB staging tile and comes back as (row, 4 features) per lane: 8 consecutive lanes cover
+                // 128 contiguous bytes of one accumulator row.
                 float4* stg = reinterpret_cast<float4*>(xs) + q * 256;      // X slots are idle once the accumulator is complete
-                const int rows_here = min(32, a.B - (mt * 128 + q * 32));
-                for (int c0 = 0; c0 < t.rows; c0 += 32) {
+                const int rows_here = min(32, a.B - row0);
+                for (int c0 = copy * 32; c0 < t.rows; c0 += 32 * a.rep) {
                   uint32_t v[32];
                   tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * t.R + c0), v);
                   tmem_ld_wait();
@@ -681,7 +689,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                     for (int r = lane >> 3; r < rows_here; r += 4) {
                       float4 val = stg[r * 8 + (g ^ (r & 7))];
                       val.x += bb.x; val.y += bb.y; val.z += bb.z; val.w += bb.w;
-                      float* dst = t.acc + (size_t)(mt * 128 + q * 32 + r) * t.ldacc + t.n0 + c0 + 4 * g;
+                      float* dst = t.acc + (size_t)(row0 + r) * t.ldacc + t.n0 + c0 + 4 * g;
                       if (!vec4) {
                         const float e[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
@@ -741,6 +749,8 @@ extern "C" int vg_decode_step(const vg_decode_step_args* a, vg_stream_t stream) 
              "vg_decode_step: batch %d / padded %d (power of two in [16,256])", a->B, a->Bp);
   VG_REQUIRE(a->NP >= 1 && a->NP <= 128 && a->grid >= 1, -3, "vg_decode_step: bad phase count / grid");
   VG_REQUIRE(a->nsplit >= 1 && a->nsplit <= 64, -3, "vg_decode_step: nsplit must be in [1,64]");
+  VG_REQUIRE((a->rep == 1 || a->rep == 2 || a->rep == 4) && (a->rep == 1 || (a->B * a->rep <= 128 && a->Bp == 128)), -3,
+             "vg_decode_step: rep %d copies of %d rows do not fit a 128-row tile", a->rep, a->B);
   const size_t smem = vg_decode_step_smem_bytes(a->NP);
   VG_REQUIRE(smem <= 227 * 1024, -6, "vg_decode_step: %d phases need %zu bytes of shared memory", a->NP, smem);
   static int sms = 0;

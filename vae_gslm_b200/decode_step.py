@@ -103,7 +103,7 @@ class _Args(C.Structure):
         ("inv_d", C.c_float), ("eps", C.c_float), ("scale", C.c_float),
         ("NP", C.c_int32), ("grid", C.c_int32), ("B", C.c_int32), ("Bp", C.c_int32), ("H", C.c_int32),
         ("Tmax", C.c_int32), ("nsplit", C.c_int32), ("barrier_mode", C.c_int32), ("advance_pos", C.c_int32),
-        ("attn_coop", C.c_int32),
+        ("rep", C.c_int32), ("attn_coop", C.c_int32),
     ]
 
 
@@ -122,10 +122,11 @@ class DecodeStepEngine:
         assert d == H * 64, "head dim 64"
         self.nheads, self.dim = H, d
         B = batch
-        Bp = 16
-        while Bp < B:
-            Bp *= 2
+        # rows of the X tile (the M operand): 128 or 256.  Up to 64 sequences the batch rows are REPLICATED into the other
+        # TMEM lane quadrants (rows b + i * 128 / rep) so that all four epilogue warps hold the results and split the columns
+        Bp = 128 if B <= 128 else 256
         self.Bp = Bp
+        self.rep = 4 if B <= 32 else (2 if B <= 64 else 1)
         sms = torch.cuda.get_device_properties(device).multi_processor_count if torch.device(device).type == "cuda" else GRID_MAX
         G = grid or min(GRID_MAX, sms)
         assert G >= UNITS, "the unit decomposition assumes at least 128 SMs"
@@ -328,7 +329,7 @@ class DecodeStepEngine:
         a.inv_d, a.eps, a.scale = 1.0 / self.dim, self.eps, 1.0 / 8.0
         a.NP, a.grid, a.B, a.Bp, a.H = self.NP, self.grid, self.batch, self.Bp, self.nheads
         a.Tmax, a.nsplit, a.barrier_mode, a.advance_pos = cache.max_len, self.nsplit, self.barrier_mode, advance
-        a.attn_coop = self.attn_coop
+        a.rep, a.attn_coop = self.rep, self.attn_coop
         return a
 
     @torch.no_grad()
