@@ -15,8 +15,35 @@ constexpr int DD = 64;            // head dim
 constexpr int DEC_WARPS = 4;
 constexpr int DEC_GROUPS = DEC_WARPS * 4;   // key groups per CTA iteration (8 lanes each)
 
+// 8 elements of a row as loaded (16 bytes of bf16 / 32 bytes of f32): kept raw while several keys are in flight
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = r; }
+  __device__ __forceinline__ void zero() { r = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = a; *reinterpret_cast<float4*>(p + 4) = b;
+  }
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
 template <typename T>
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+__global__ void __launch_bounds__(DEC_WARPS * 32, 6)
 attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __restrict__ v_cache,
                    T* __restrict__ out, float* __restrict__ partial, const float* __restrict__ slopes,
                    int H, int Tmax, int pos_arg, const int32_t* __restrict__ pos_dev, int splits, float scale,
@@ -53,40 +80,52 @@ attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __rest
   for (int d = 0; d < 8; ++d) acc[d] = 0.f;
 
   // the trip count is CTA-uniform and out-of-range key groups are predicated: the 8-lane shuffles below use the
-  // full-warp mask, so every lane of a warp must reach them together
-  for (int base = j_begin; base < j_end; base += DEC_GROUPS) {
-    const int j = base + grp;
-    const bool active = j < j_end;
-    Vec8<T> kv8, vv8;
-    if (active) {
-      if (j == pos) {
-        kv8.load(knew + sub * 8);
-        vv8.load(vnew + sub * 8);
-        kv8.store(kc + (int64_t)pos * DD + sub * 8);      // append (fused kv-cache write)
-        vv8.store(vc + (int64_t)pos * DD + sub * 8);
+  // full-warp mask, so every lane of a warp must reach them together.  DEC_UNROLL keys per group are loaded before any
+  // is consumed: with one key per iteration the kernel ran at 4.3 TB/s at batch 256 (profiles/r02_decode.md) — the
+  // scores of key j gate the loads of key j + 16.
+  constexpr int DEC_UNROLL = 4;
+  for (int base = j_begin; base < j_end; base += DEC_GROUPS * DEC_UNROLL) {
+    Raw8<T> kraw[DEC_UNROLL], vraw[DEC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      const int j = base + u * DEC_GROUPS + grp;
+      if (j < j_end) {
+        if (j == pos) {
+          kraw[u].load(knew + sub * 8);
+          vraw[u].load(vnew + sub * 8);
+          kraw[u].store(kc + (int64_t)pos * DD + sub * 8);      // append (fused kv-cache write)
+          vraw[u].store(vc + (int64_t)pos * DD + sub * 8);
+        } else {
+          kraw[u].load(kc + (int64_t)j * DD + sub * 8);
+          vraw[u].load(vc + (int64_t)j * DD + sub * 8);
+        }
       } else {
-        kv8.load(kc + (int64_t)j * DD + sub * 8);
-        vv8.load(vc + (int64_t)j * DD + sub * 8);
+        kraw[u].zero();
+        vraw[u].zero();
       }
-    } else {
-#pragma unroll
-      for (int d = 0; d < 8; ++d) { kv8.v[d] = 0.f; vv8.v[d] = 0.f; }
     }
-    float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < 8; ++d) s = fmaf(qv.v[d], kv8.v[d], s);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (active) {
-      s = s * scale - slope * (float)(pos - j);
-      const float mnew = fmaxf(m, s);
-      const float corr = expf(m - mnew);      // m = -inf on first key → 0
-      const float p = expf(s - mnew);
-      l = l * corr + p;
+    for (int u = 0; u < DEC_UNROLL; ++u) {
+      const int j = base + u * DEC_GROUPS + grp;
+      float kf[8], vf[8];
+      kraw[u].unpack(kf);
+      float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < 8; ++d) acc[d] = acc[d] * corr + p * vv8.v[d];
-      m = mnew;
+      for (int d = 0; d < 8; ++d) s = fmaf(qv.v[d], kf[d], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (j < j_end) {
+        s = s * scale - slope * (float)(pos - j);
+        const float mnew = fmaxf(m, s);
+        const float corr = expf(m - mnew);      // m = -inf on first key → 0
+        const float p = expf(s - mnew);
+        l = l * corr + p;
+        vraw[u].unpack(vf);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc[d] = acc[d] * corr + p * vf[d];
+        m = mnew;
+      }
     }
   }
   if (sub == 0) { sm_m[grp] = m; sm_l[grp] = l; }

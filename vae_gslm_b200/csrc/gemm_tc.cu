@@ -132,6 +132,18 @@ static TcPlan pick_plan(const vg_gemm_args* a) {
   const bool can_split = splitk_eligible(a);
   static const int env_pair = getenv("VG_GEMM_PAIR") ? atoi(getenv("VG_GEMM_PAIR")) : 1;
   if (a->N <= 64) return TcPlan{64, 1, 0};
+  if (a->M <= 256 && !env_bn && !env_splits) {
+    // Skinny problems (the cached generation step at batch <= 256: M = batch): HBM-bound on the weights, so what matters
+    // is that ALL SMs stream a share of W.  128 x 64 tiles give the most units; when the epilogue is a pure f32
+    // accumulation (out-proj / FFN2 reducing into the fp32 residual stream) the k-range is split until the grid is full
+    // (>= 2 k-blocks per unit).  Measured per shape in profiles/r02_decode.md.
+    const int bn = a->N >= 512 ? 64 : 128;
+    const int64_t tiles = ceil_div(a->M, TBM) * ceil_div(a->N, bn);
+    int s = 1;
+    if (can_split)
+      while (tiles * s * 2 <= gemm_sm_budget() && num_kb / (s * 2) >= 2) s *= 2;
+    return TcPlan{bn, s, 0};
+  }
   TcPlan best{128, 1, 0};
   double best_cost = 1e30;
   for (int bn = 128; bn <= 256; bn *= 2) {

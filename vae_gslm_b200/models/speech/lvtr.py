@@ -100,9 +100,13 @@ class LVTR(nn.Module):
         # ... up to this batch: measured on B200 (profiles/r01_decode.md) the weight-streaming engine wins up to ~100
         # sequences (0.47 vs 1.21 ms per step at B=1, 1.02 vs 1.37 at 64), the tcgen05 layer-by-layer path above
         self.decode_engine_max_batch = 96
-        # "step": the persistent single-launch kernel (decode_step.py, any batch <= 256); "linear": round 1's
-        # kernel-per-linear engine (decode.py, batch <= decode_engine_max_batch)
-        self.decode_engine_kind = "step"
+        # Which engine runs a bf16 single-frame step.  Measured on B200 over the configured generation (3 s prompt →
+        # 10 s, mean 402 cached keys; profiles/r02_decode.md), ms per step for step / linear / layer-by-layer:
+        #   batch 1: 0.47 / 0.54 / 1.2     8: 0.53 / 0.74 / -     32: 0.85 / 0.89 / -     64: 1.41 / 1.24 / 1.42
+        #   128: 2.33 / - / 1.71     256: 4.27 / - / 2.26
+        # "auto" = the persistent single-launch kernel (decode_step.py) up to 32 sequences, round 1's kernel-per-linear
+        # engine (decode.py) up to 80, the tcgen05 layer-by-layer path above.  "step" / "linear" force one engine.
+        self.decode_engine_kind = "auto"
 
     # ------------------------------------------------------------------ configuration
     def set_compute_dtype(self, dtype: torch.dtype) -> "LVTR":
@@ -327,12 +331,16 @@ class LVTR(nn.Module):
                 or past_kv is None or not isinstance(past_kv[0], LayerKV) or not u.is_cuda
                 or self.compute_dtype != torch.bfloat16):
             return None
-        step_kind = self.decode_engine_kind == "step"
-        if u.shape[0] > (256 if step_kind else self.decode_engine_max_batch):
+        nb = u.shape[0]
+        kind = self.decode_engine_kind
+        if kind == "auto":
+            kind = "step" if nb <= 32 else ("linear" if nb <= 80 else "none")
+        step_kind = kind == "step"
+        if kind == "none" or nb > (256 if step_kind else self.decode_engine_max_batch):
             return None
         engines = self.__dict__.setdefault("_decode_engines", {})
         stack = self.transformer[0]
-        stamp = (self.decode_engine_kind,) + tuple(p._version for p in stack.parameters())   # rebuilt after a weight update
+        stamp = (kind,) + tuple(p._version for p in stack.parameters())   # rebuilt after a weight update
         ent = engines.get(u.shape[0])
         if ent is None or ent[0] != stamp:
             if step_kind:
