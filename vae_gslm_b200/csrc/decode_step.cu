@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
               for (int mt = 0; mt < mtiles; ++mt) {
                 const int row0 = mt * 128 + qrow;
                 if (row0 >= a.B) break;
-                const bool vec4 = (t.ldacc & 3) == 0;            // 16-byte vector atomics need 16-byte aligned rows
+                const bool vec4 = ((t.ldacc | t.rows) & 3) == 0;  // 16-byte vector atomics: 16-byte aligned rows, whole groups
                 // 32 columns at a time: thread = batch row (TMEM lane) holds 32 consecutive features.  One lane per row
                 // issuing the atomics is slow when few rows are valid, so the chunk goes through a warp-private,
                 // XOR-swizzled 4 KB staging tile and comes back as (row, 4 features) per lane: 8 consecutive lanes cover
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                   }
                   __syncwarp();
                   const int g = lane & 7;
-                  if (c0 + 4 * g < t.rows) {                    // rows is a multiple of 4
+                  if (c0 + 4 * g < t.rows) {
                     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (t.bias_out) bb = *reinterpret_cast<const float4*>(&sh.bias[par][c0 + 4 * g]);
                     for (int r = lane >> 3; r < rows_here; r += 4) {
@@ -693,7 +693,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_step_kernel(const __grid
                       if (!vec4) {
                         const float e[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { if (t.store) __stcg(dst + i, e[i]); else ds_red_add(dst + i, e[i]); }
+                        for (int i = 0; i < 4; ++i) {
+                          if (c0 + 4 * g + i >= t.rows) break;       // ragged tail of the last feature slab
+                          if (t.store) __stcg(dst + i, e[i]); else ds_red_add(dst + i, e[i]);
+                        }
                       } else if (t.store) {
                         __stcg(reinterpret_cast<float4*>(dst), val);
                       } else {
