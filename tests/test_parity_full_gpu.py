@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CFG = os.path.join(ROOT, "vae_gslm_b200", "configs", "train", "speech", "vae-gslm.yaml")
 
 # bf16 gradient bound: O.bf16_grad_within_bound (oracle/lvtr_oracle.py) — per tensor within 2e-2 of the fp32 oracle gradient or
-# no noisier than 2 x the oracle under torch.autocast(bf16); the same function is asserted by __graft_entry__.smoke()
+# no noisier than 2.5 x the oracle under torch.autocast(bf16); the same function is asserted by __graft_entry__.smoke()
 BF16_GRAD_BOUND = O.BF16_GRAD_BOUND
 
 

@@ -26,6 +26,10 @@ from . import _lib as L
 _ALIGN = 64      # elements; keeps every tensor 256-byte aligned inside the arena (TMA needs 16 B)
 
 
+def _capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 def execution_order(model: nn.Module) -> List[Tuple[str, nn.Parameter]]:
     """parameters in (approximate) forward execution order, so that backward completes buckets back to front."""
     prefixes = ["encoder.", "token_embedding.", "token_fuser.", "transformer.0.", "q_spliter.", "token_spliter.",
@@ -82,10 +86,21 @@ class ParamArena:
         self.nodecay = _Group([(n, p) for n, p in items if p.ndim == 1], device, 0.0, False)
         self.groups = [self.decay, self.nodecay]
         self.step_count = 0
+        # bumped whenever parameter VALUES change behind torch's back (the fused AdamW writes through raw pointers and
+        # does not touch Tensor._version): inference-side memos of derived weights (LVTR._cat, the decode engines'
+        # packed / concatenated copies) key on it
+        self.generation = 0
+        model.__dict__["_vg_param_arena"] = self
         self.micro_batch = 0          # index inside the current accumulation window (0 → wgrad overwrites)
         self.hyper = [torch.zeros(4, dtype=torch.float32, device=device) for _ in self.groups]
-        self._hyper_host = [torch.zeros(4, dtype=torch.float32).pin_memory() if torch.cuda.is_available()
-                            else torch.zeros(4) for _ in self.groups]
+        # pinned staging of {lr, 1/bc1, 1/sqrt(bc2), 1-lr*wd}: a ring of _HYPER_DEPTH buffers per group, one per step, so
+        # that a host running ahead of the GPU never overwrites values whose (stream-ordered, asynchronous) upload has not
+        # executed yet; upload_hyper() guards the reuse of a ring entry with an event
+        pin = torch.cuda.is_available()
+        self._hyper_ring = [[torch.zeros(4, dtype=torch.float32).pin_memory() if pin else torch.zeros(4)
+                             for _ in self.groups] for _ in range(self._HYPER_DEPTH)]
+        self._hyper_events = [None] * self._HYPER_DEPTH
+        self._hyper_host = self._hyper_ring[0]
         self.on_grad_ready = None     # dp.py installs a callback(param) here
         # Every parameter carries a handle to its gradient slice: the ops that produce parameter gradients on the hot
         # path (wgrad GEMMs, bias column sums, RMSNorm scale sums — ops._wgrad / ops._bgrad / ops._RMSNorm) ACCUMULATE
@@ -116,6 +131,7 @@ class ParamArena:
     # projections on the accumulate path: their weight-gradient GEMMs run split-K (red.global.add into C), which
     # would need its own clear of C for beta = 0.
     _BIG = 3 << 19
+    _HYPER_DEPTH = 4
 
     def calibrate_next(self) -> None:
         """observe, during the next step, which parameters receive their gradient only through wgrad_beta() sites.
@@ -197,13 +213,10 @@ class ParamArena:
                    grad_scale: float = 1.0, use_device_hyper: bool = False) -> None:
         """torch.optim.AdamW semantics over both arenas; refreshes the bf16 shadows in the same pass."""
         bc1, bc2 = self.stage_hyper(lr, beta1, beta2)
-        for grp, hyper, host in zip(self.groups, self.hyper, self._hyper_host):
-            hp = None
-            if use_device_hyper:
-                # the copy node reads the pinned host buffer at EXECUTION time, so a captured graph picks up
-                # whatever stage_hyper() wrote before each replay
-                hyper.copy_(host, non_blocking=True)
-                hp = L.ptr(hyper)
+        if use_device_hyper and not _capturing():
+            self.upload_hyper()
+        for grp, hyper in zip(self.groups, self.hyper):
+            hp = L.ptr(hyper) if use_device_hyper else None
             L.call("vg_adamw_step", L.ptr(grp.p), L.ptr(grp.g), L.ptr(grp.m), L.ptr(grp.v),
                    L.ptr(grp.shadow) if grp.shadow is not None else None, grp.numel, lr, beta1, beta2, eps,
                    grp.weight_decay, bc1, bc2, grad_scale, hp, L.stream())
@@ -211,11 +224,28 @@ class ParamArena:
     def stage_hyper(self, lr: float, beta1: float = 0.9, beta2: float = 0.98):
         """advance the step counter and write {lr, 1/bc1, 1/sqrt(bc2), 1-lr*wd} to the pinned staging buffers."""
         self.step_count += 1
+        self.generation += 1
         bc1 = 1.0 - beta1 ** self.step_count
         bc2 = 1.0 - beta2 ** self.step_count
+        k = self.step_count % self._HYPER_DEPTH
+        ev = self._hyper_events[k]
+        if ev is not None:
+            ev.synchronize()                      # the upload that last read this ring entry has executed
+        self._hyper_host = self._hyper_ring[k]
         for grp, host in zip(self.groups, self._hyper_host):
             host[0], host[1], host[2], host[3] = lr, 1.0 / bc1, bc2 ** -0.5, 1.0 - lr * grp.weight_decay
         return bc1, bc2
+
+    def upload_hyper(self) -> None:
+        """enqueue, on the current stream and OUTSIDE any captured graph, the copy of the staged scalars to the device
+        buffers the AdamW kernels read (use_device_hyper): stream order puts it after the previous step's kernels and
+        before this step's, whatever the host's lead over the GPU."""
+        for hyper, host in zip(self.hyper, self._hyper_host):
+            hyper.copy_(host, non_blocking=True)
+        if torch.cuda.is_available() and self.hyper[0].is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._hyper_events[self.step_count % self._HYPER_DEPTH] = ev
 
     # ------------------------------------------------------------------ data-parallel buckets
     def buckets(self, bucket_bytes: int = 64 << 20) -> List[Tuple[torch.Tensor, List[nn.Parameter]]]:
@@ -237,9 +267,8 @@ class ParamArena:
         """advance the step counter and stage this step's scalars; must precede the first adamw_bucket()."""
         self._bc = self.stage_hyper(lr, beta1, beta2)
         self._step_args = (lr, beta1, beta2, use_device_hyper)
-        if use_device_hyper:
-            for hyper, host in zip(self.hyper, self._hyper_host):
-                hyper.copy_(host, non_blocking=True)
+        if use_device_hyper and not _capturing():
+            self.upload_hyper()                   # (a captured step gets its scalars uploaded before each replay)
 
     def adamw_bucket(self, bucket_index: int, eps: float = 1e-8, grad_scale: float = 1.0) -> None:
         """AdamW (+ bf16 shadow refresh) of ONE bucket of buckets(): lets the optimizer run, bucket by bucket, as soon as
@@ -269,8 +298,27 @@ class ParamArena:
                                "exp_avg_sq": grp.v[o:o + n].view(p.shape).detach().cpu().clone()}
         return {"step": self.step_count, "state": state}
 
+    def snapshot(self) -> Dict[str, object]:
+        """parameters, moments, shadows and the step count — TrainStep takes one before its calibration / warm-up / capture
+        steps (real optimizer updates on the example batch) and restores it afterwards, so that building a TrainStep leaves
+        a freshly initialised or just-resumed model exactly as it found it."""
+        return {"step": self.step_count,
+                "groups": [(g.p.clone(), g.m.clone(), g.v.clone(), g.shadow.clone() if g.shadow is not None else None)
+                           for g in self.groups]}
+
+    def restore(self, snap: Dict[str, object]) -> None:
+        self.step_count = int(snap["step"])
+        self.generation += 1
+        for g, (p, m, v, sh) in zip(self.groups, snap["groups"]):
+            g.p.copy_(p)
+            g.m.copy_(m)
+            g.v.copy_(v)
+            if sh is not None:
+                g.shadow.copy_(sh)
+
     def load_optimizer_state_dict(self, sd: Dict[str, object]) -> None:
         self.step_count = int(sd["step"])
+        self.generation += 1
         for grp in self.groups:
             for name, p, o in zip(grp.names, grp.params, grp.offsets):
                 n = p.numel()
@@ -280,6 +328,7 @@ class ParamArena:
 
     def refresh_shadow(self) -> None:
         """re-derive the bf16 weight shadows after parameters were loaded into the arena (model.load_state_dict)."""
+        self.generation += 1
         for grp in self.groups:
             if grp.shadow is not None:
                 L.call("vg_cast_f32_to_bf16", L.ptr(grp.p), L.ptr(grp.shadow), grp.numel, L.stream())

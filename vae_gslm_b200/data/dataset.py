@@ -180,24 +180,35 @@ class TokenMelDataset(torch.utils.data.Dataset):
         return pad_to_max_length(batch, self.post_pad())
 
 
+class PinnedBatch(dict):
+    """one pinned host slot of the BatchAssembler; ``event`` is set by ``TrainStep.load`` behind the asynchronous H2D
+    copies that read it, and waited for before the slot is refilled"""
+    event = None
+
+
 class BatchAssembler:
     """collate straight into pinned, reusable host buffers in the layout the training step consumes:
     ``x [B,T,1+n_mels]`` (token id as float ⊕ mel, trainers/speech/lvtr.py:117-118), ``mask [B,T]``,
     ``utterance [B,Tu,n_mels]``, ``utt_mask [B,Tu]``.  ``depth`` buffers rotate so that the copy of batch i can be in
-    flight while batch i+1 is assembled."""
+    flight while batch i+1 is assembled; a slot is not refilled before the copies that read it have executed (the
+    consumer — ``TrainStep.load`` — leaves a CUDA event in ``slot.event``; the host may be several replays ahead)."""
 
     def __init__(self, batch_size: int, frames: int, utt_frames: int, n_mels: int, depth: int = 2,
                  pin: Optional[bool] = None) -> None:
         pin = torch.cuda.is_available() if pin is None else pin
         mk = (lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt).pin_memory() if pin else torch.zeros(*s, dtype=dt))
-        self.slots = [dict(x=mk(batch_size, frames, 1 + n_mels), mask=mk(batch_size, frames, dt=torch.bool),
-                           utterance=mk(batch_size, utt_frames, n_mels), utt_mask=mk(batch_size, utt_frames, dt=torch.bool))
+        self.slots = [PinnedBatch(x=mk(batch_size, frames, 1 + n_mels), mask=mk(batch_size, frames, dt=torch.bool),
+                                  utterance=mk(batch_size, utt_frames, n_mels),
+                                  utt_mask=mk(batch_size, utt_frames, dt=torch.bool))
                       for _ in range(depth)]
         self.next = 0
 
     def __call__(self, items: List[Mapping[str, torch.Tensor]], utt_key: str = "cropped_mel_utt") -> Dict[str, torch.Tensor]:
         slot = self.slots[self.next]
         self.next = (self.next + 1) % len(self.slots)
+        if slot.event is not None:
+            slot.event.synchronize()              # the H2D copies of the batch last assembled here have executed
+            slot.event = None
         B, T, _ = slot["x"].shape
         Tu = slot["utterance"].shape[1]
         assert len(items) <= B

@@ -125,11 +125,13 @@ class GradReducer:
     def finish(self) -> None:
         """reduce whatever has not been launched yet (parameters unused in this step never fire a hook) and make
         the compute stream wait for the collectives."""
+        if getattr(self, "_calibrating", False):
+            # (also when nothing was armed — world 1 without a bucket-wise optimizer: the flag must not outlive its step)
+            self._calibrating = False
+            if self.enabled:
+                self._size = [sum(self._seen.get(id(p), 0) for p in members) for _, members in self.buckets]
         if not self.enabled:
             return
-        if getattr(self, "_calibrating", False):
-            self._calibrating = False
-            self._size = [sum(self._seen.get(id(p), 0) for p in members) for _, members in self.buckets]
         for bi in range(len(self.buckets)):
             self._launch(bi)
         if self.is_cuda:

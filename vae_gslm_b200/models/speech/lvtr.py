@@ -145,13 +145,19 @@ class LVTR(nn.Module):
         source parameter changes, so the decode loop does not re-concatenate (or re-cast) every step."""
         if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
             return torch.cat(list(tensors), dim)
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        key = (self._weights_generation(),) + tuple((t.data_ptr(), t._version) for t in tensors)
         memo = self.__dict__.setdefault("_cat_memo", {})
         hit = memo.get(name)
         if hit is None or hit[0] != key:
             hit = (key, torch.cat([t.detach() for t in tensors], dim))
             memo[name] = hit
         return hit[1]
+
+    def _weights_generation(self) -> int:
+        """counter of parameter updates torch cannot see (ParamArena's fused AdamW writes through raw pointers and leaves
+        Tensor._version alone): part of every key under which derived weights are memoised"""
+        arena = self.__dict__.get("_vg_param_arena")
+        return arena.generation if arena is not None else 0
 
     def _split_weights(self):
         wq, wt = self.q_spliter.linear, self.token_spliter.linear
@@ -340,7 +346,8 @@ class LVTR(nn.Module):
             return None
         engines = self.__dict__.setdefault("_decode_engines", {})
         stack = self.transformer[0]
-        stamp = (kind,) + tuple(p._version for p in stack.parameters())   # rebuilt after a weight update
+        # rebuilt after a weight update, seen by torch (_version) or not (the arena's generation counter)
+        stamp = (kind, self._weights_generation()) + tuple(p._version for p in stack.parameters())
         ent = engines.get(u.shape[0])
         if ent is None or ent[0] != stamp:
             if step_kind:

@@ -114,6 +114,8 @@ class TransformerLayerStack(nn.Module):
 
     def run(self, tgt: TensorMask, memory: Optional[TensorMask] = None, past_kv: Optional[List] = None,
             return_attn: bool = False, return_kv: bool = False) -> Mapping[str, Any]:
+        from ...utils.tensormask import new_pass
+        new_pass()                                  # sequence lengths memoised on the mask tensor are per-pass
         outputs = {"output": []}
         if return_attn:
             outputs["self_attn"] = []

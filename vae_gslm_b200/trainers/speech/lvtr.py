@@ -77,22 +77,40 @@ def make_model_input(tokens: TensorMask, mel: TensorMask) -> TensorMask:
 
 
 class TrainStep:
-    """zero-grad → forward → loss → backward → gradient all-reduce → fused AdamW, on static input buffers.
+    """zero-grad → [forward → loss → backward] x ``accumulate`` micro-batches → gradient all-reduce → fused AdamW, on
+    static input buffers.
 
-    With ``use_cuda_graph`` the whole sequence (≈5,000 kernel launches: ours, cuDNN/cuBLAS for the conv stack,
-    NCCL) is captured ONCE and replayed, which removes the Python/launch overhead that otherwise bounds the step.
-    Per-step scalars that change (learning rate, Adam bias corrections, KL weight) live in device memory and are
-    refreshed from pinned host memory by copy nodes inside the graph.
+    ``accumulate`` is the recipe's ``training.gradient_accumulation`` (2 in configs/train/speech/vae-gslm.yaml): as in the
+    reference's manual optimisation (trainers/speech/lvtr.py:147-158; training_lib/trainer.py:17-20) the UNSCALED losses of
+    the micro-batches are back-propagated into the same gradients and the optimizer / LR schedule / KL schedule advance once
+    per window; the data-parallel all-reduce runs on the last micro-batch only.
+    With ``use_cuda_graph`` the whole sequence (≈5,000 kernel launches per micro-batch: ours, cuDNN for the utterance
+    encoder, NCCL) is captured ONCE and replayed, which removes the Python/launch overhead that otherwise bounds the step.
+    Per-step scalars that change (learning rate, Adam bias corrections, KL weight) live in device memory; they are staged
+    in rotating pinned host buffers and uploaded by ordinary stream-ordered copies issued before each replay (never from
+    inside the graph: a copy node would read the host buffer when it EXECUTES, by which time a host running ahead may
+    have staged the next step's values).
+    Building a TrainStep runs a calibration step, warm-up steps and the capture on the example batch; the arena is
+    snapshotted before and restored after, so a fresh or just-resumed model is left exactly as it was found.
     """
 
     def __init__(self, model, arena, reducer, example_batch: Dict[str, torch.Tensor], *, lr: float,
                  kld_weight: float = 0.04, betas=(0.9, 0.98), eps: float = 1e-8, use_cuda_graph: bool = True,
-                 warmup_iters: int = 3, overlap_grads: bool = True) -> None:
+                 warmup_iters: int = 3, overlap_grads: bool = True, accumulate: int = 1,
+                 preserve_state: bool = True) -> None:
         self.model, self.arena, self.reducer = model, arena, reducer
         self.lr, self.betas, self.eps = lr, betas, eps
-        self.static = {k: v.clone() for k, v in example_batch.items()}        # device-resident input buffers
+        self.accumulate = int(accumulate)
+        assert self.accumulate >= 1
+        # device-resident input buffers, one set per micro-batch of the accumulation window
+        self.statics = [{k: v.clone() for k, v in example_batch.items()} for _ in range(self.accumulate)]
+        self.static = self.statics[0]
         dev = next(iter(self.static.values())).device
         self.kw_dev = torch.full((), float(kld_weight), device=dev)
+        self._kw_ring = [torch.full((), float(kld_weight)).pin_memory() if dev.type == "cuda" else torch.full((), float(kld_weight))
+                         for _ in range(4)]
+        self._kw_events = [None] * 4
+        self._kw_i = 0
         self.loss = torch.zeros((), device=dev)
         self.terms = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -107,15 +125,18 @@ class TrainStep:
         # another stream would be invalidated.
         self.stream = torch.cuda.Stream(device=dev)
         from ... import _lib
+        snap = arena.snapshot() if (preserve_state and hasattr(arena, "snapshot")) else None
         n0 = _lib.launch_count
         if hasattr(self.reducer, "calibrate_next"):
             self.reducer.calibrate_next()                   # first step: learn how often each gradient is announced
         if hasattr(self.arena, "calibrate_next"):
             self.arena.calibrate_next()                     # … and which gradients are only ever written directly
+        acc, self.accumulate = self.accumulate, 1           # calibration counts announcements of ONE micro-batch
         self._run_eager(device_hyper=False)                 # also the first warm-up iteration
+        self.accumulate = acc
         if hasattr(self.arena, "finish_calibration"):
             self.arena.finish_calibration()
-        self.launches_per_step = _lib.launch_count - n0     # libvgslm kernels per step (bench.py's gpu_launches)
+        self.launches_per_step = (_lib.launch_count - n0) * self.accumulate   # libvgslm kernels per step (gpu_launches)
         if use_cuda_graph:
             try:
                 self._capture(warmup_iters)
@@ -123,6 +144,9 @@ class TrainStep:
             except Exception as e:      # NB: a failed capture leaves torch's RNG in capture mode; callers restart
                 self.graph = None
                 self.capture_error = repr(e)
+        if snap is not None:
+            torch.cuda.synchronize(dev) if dev.type == "cuda" else None
+            arena.restore(snap)
 
     def _run_eager(self, device_hyper: bool, serial: bool = False) -> None:
         """one eager step; ``serial`` switches every stream overlap off (bench.py's per-kernel timing pass)."""
@@ -140,7 +164,6 @@ class TrainStep:
 
     # the work of one step, on whatever stream is current
     def _body(self, device_hyper: bool) -> None:
-        s = self.static
         from ... import ops
         if self.grad_stream is None and self.loss.is_cuda and self.overlap_grads:
             self.grad_stream = torch.cuda.Stream(device=self.loss.device)
@@ -153,17 +176,26 @@ class TrainStep:
             # bucket-wise AdamW on the communication stream, right behind each bucket's all-reduce
             self.arena.begin_step(self.lr, self.betas[0], self.betas[1], use_device_hyper=device_hyper)
             self.reducer.after_bucket = lambda bi: self.arena.adamw_bucket(bi, eps=self.eps)
-        self.reducer.prepare(last_micro_batch=True)
-        out = self.model(TensorMask(s["x"], s["mask"]), utterance=TensorMask(s["utterance"], s["utt_mask"]))
-        terms = assemble_loss(out, kld_weight=self.kw_dev)
-        terms["loss"].backward()
+        total = None
+        for mb in range(self.accumulate):
+            s = self.statics[mb]
+            last = mb == self.accumulate - 1
+            self.reducer.prepare(last_micro_batch=last)       # the collective (and the bucket-wise AdamW) only on the last
+            out = self.model(TensorMask(s["x"], s["mask"]), utterance=TensorMask(s["utterance"], s["utt_mask"]))
+            terms = assemble_loss(out, kld_weight=self.kw_dev)
+            terms["loss"].backward()                          # unscaled, as the reference's manual_backward(loss)
+            total = terms["loss"].detach() if total is None else total + terms["loss"].detach()
+            if not last:
+                self.arena.end_micro_batch()
+                if self.grad_stream is not None:
+                    torch.cuda.current_stream().wait_stream(self.grad_stream)
         ops.GRAD_STREAM = None
         if self.grad_stream is not None:
             torch.cuda.current_stream().wait_stream(self.grad_stream)     # parameter gradients are complete
         self.reducer.finish()
         if not self.overlap_optimizer:
             self.arena.adamw_step(self.lr, self.betas[0], self.betas[1], self.eps, use_device_hyper=device_hyper)
-        self.loss.copy_(terms["loss"].detach())
+        self.loss.copy_(total)
 
     def _capture(self, warmup_iters: int) -> None:
         for _ in range(warmup_iters):                      # warm-up off the default stream, as torch requires
@@ -175,16 +207,38 @@ class TrainStep:
             self._body(device_hyper=True)
         self.arena.step_count = steps_before               # capture advanced the host counter without running
 
-    def load(self, batch: Dict[str, torch.Tensor]) -> None:
-        """copy a (pinned host or device) batch into the static input buffers."""
+    def load(self, batch: Dict[str, torch.Tensor], micro_batch: int = 0) -> None:
+        """copy a (pinned host or device) batch into the static input buffers of one micro-batch.  If the batch carries an
+        ``event`` attribute (data.dataset.PinnedBatch) an event recorded behind the copies is stored there: the assembler
+        waits for it before it refills that pinned slot."""
+        dst = self.statics[micro_batch]
         for k, v in batch.items():
-            self.static[k].copy_(v, non_blocking=True)
+            dst[k].copy_(v, non_blocking=True)
+        if hasattr(batch, "event") and self.loss.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            batch.event = ev
 
-    def __call__(self, lr: Optional[float] = None) -> torch.Tensor:
+    def set_kld_weight(self, kld_weight: float) -> None:
+        """stage this step's KL weight (kld_weight_at(global_step, …), trainers/speech/lvtr.py:104-110) and enqueue its upload"""
+        k = self._kw_i = (self._kw_i + 1) % len(self._kw_ring)
+        if self._kw_events[k] is not None:
+            self._kw_events[k].synchronize()
+        self._kw_ring[k].fill_(float(kld_weight))
+        self.kw_dev.copy_(self._kw_ring[k], non_blocking=True)
+        if self.loss.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._kw_events[k] = ev
+
+    def __call__(self, lr: Optional[float] = None, kld_weight: Optional[float] = None) -> torch.Tensor:
         if lr is not None:
             self.lr = lr
+        if kld_weight is not None:
+            self.set_kld_weight(kld_weight)
         if self.graph is not None:
-            self.arena.stage_hyper(self.lr, self.betas[0], self.betas[1])     # pinned values read by the graph
+            self.arena.stage_hyper(self.lr, self.betas[0], self.betas[1])     # rotating pinned staging …
+            self.arena.upload_hyper()                                         # … uploaded in stream order, before the replay
             self.graph.replay()
         else:
             self._run_eager(device_hyper=False)

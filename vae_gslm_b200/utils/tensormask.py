@@ -12,6 +12,16 @@ from typing import List, Optional, Tuple, Union
 import torch
 
 
+_PASS = [0]
+
+
+def new_pass() -> None:
+    """called at the start of every transformer-stack pass: lengths memoised on a mask tensor (``lengths_i32``) are valid
+    for ONE pass only.  Static input buffers are refilled in place between steps (TrainStep.load), and a CUDA-graph capture
+    must contain the reduction itself, not a tensor memoised during warm-up."""
+    _PASS[0] += 1
+
+
 class TensorMask(object):
     def __init__(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, axis: int = 1) -> None:
         if axis not in (1, 2):
@@ -46,14 +56,17 @@ class TensorMask(object):
         return self.mask.contiguous().view(torch.uint8).reshape(-1)
 
     def lengths_i32(self) -> torch.Tensor:
-        cached = getattr(self.mask, "_vg_lengths", None)        # memoised on the mask tensor: one reduction per batch
-        if cached is None:
-            cached = self.mask.sum(-1, dtype=torch.int32)
-            try:
-                self.mask._vg_lengths = cached
-            except Exception:
-                pass
-        return cached
+        # memoised on the mask tensor for the current pass (16 layers share one mask): one reduction per pass
+        key = (_PASS[0], self.mask._version)
+        cached = getattr(self.mask, "_vg_lengths", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        lengths = self.mask.sum(-1, dtype=torch.int32)
+        try:
+            self.mask._vg_lengths = (key, lengths)
+        except Exception:
+            pass
+        return lengths
 
     # ------------------------------------------------------------------ masking
     def apply_mask(self, mask_value: float = 0) -> "TensorMask":
