@@ -206,6 +206,8 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all instances of one step)",
                 "achieved": round(achieved, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["bf16_sustained"], 4), "peak_source": peaks["src"] + " sustained",
+                # the GEMMs are timed one at a time (eager, serial pass): against the BURST peak the same number reads
+                "peak_burst": peaks["bf16_burst"], "frac_vs_burst": round(achieved / peaks["bf16_burst"], 4),
                 # DRAM read+write bytes of ONE representative launch (FFN1 forward, bias+GELU+saved derivative, 8000x4096x1024)
                 # from `ncu --set full`: profiles/r01_gemm_gelu_pair_ncu.md (algorithmic bytes of that launch: 155.8e6)
                 "traffic": 112.9e6, "traffic_launch": "ffn1 fwd 8000x4096x1024 (ncu --set full, profiles/r01_gemm_gelu_pair_ncu.md)",
@@ -229,23 +231,87 @@ def run_ours(args):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "loss": float(last_loss), "step_mode": train_step.mode,
     }
+    # ---- the other BASELINE shapes on the same model / arena / reducer (new static buffers, new capture): the repo
+    #      config's shape (8 x 640 frames, configs/train/speech/vae-gslm.yaml:173-184) and configs[4] (60 s = 3000 frames)
+    if not args.no_shapes:
+        result["shapes"] = {}
+        for (b2, t2) in ((8, 640), (2, 3000)):
+            train_step.graph = None
+            res2 = {k: v.to(dev) for k, v in synthetic_batch(b2, t2, rank).items()}
+            ts2 = TrainStep(model, arena, reducer, res2, lr=lr, kld_weight=KW, use_cuda_graph=not args.no_cuda_graph)
+            if ts2.graph is None and not args.no_cuda_graph:
+                # (a failed capture leaves torch's CUDA RNG in capture mode: nothing more can run in this process)
+                result["shapes"][f"B{b2}_T{t2}"] = {"unavailable": "cuda-graph capture failed: " + str(ts2.capture_error)[:200]}
+                args.no_decode = args.no_gpu_reference = args.no_cpu_baseline = True
+                break
+            for _ in range(3):
+                ts2()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n2 = max(5, args.steps // 2)
+            e0.record()
+            for _ in range(n2):
+                ts2()
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+            v2 = b2 * t2 * world * n2 / (float(ms2) / 1e3)
+            result["shapes"][f"B{b2}_T{t2}"] = {
+                "value": round(v2, 1), "unit": "frames/s", "ms_per_step": round(float(ms2) / n2, 3), "steps": n2,
+                "per_gpu_frames_per_sec": round(v2 / world, 1), "step_mode": ts2.mode,
+                "model_tflops_per_gpu": round(train_flops_per_frame(t2) * v2 / world / 1e12, 1),
+                "mfu_vs_measured_sustained": round(train_flops_per_frame(t2) * v2 / world / 1e12 / peaks["bf16_sustained"], 4),
+                "mfu_vs_nominal_2250": round(train_flops_per_frame(t2) * v2 / world / 1e12 / 2250.0, 4)}
+            ts2.graph = None
+            del ts2, res2
+            torch.cuda.empty_cache()
+    if world > 1:
+        # data-parallel invariant: after the same number of steps every rank holds bit-identical parameters
+        chk = torch.stack([torch.stack([g.p.double().sum(), (g.p.double() ** 2).sum()]) for g in arena.groups]).reshape(-1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        result["dp_check"] = {"params_identical_across_ranks": bool(all(torch.equal(allc[0], c) for c in allc)),
+                              "checksum": [float(x) for x in allc[0]], "optimizer_steps": arena.step_count}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        result["cpu_baseline"] = cpu_baseline_sample(model, hp)
-    if rank == 0 and not args.no_decode:
-        result["decode"] = decode_bench(model, dev, peaks)
+        result["cpu_baseline"] = cpu_baseline_sample(lr)
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        train_step.graph = None
+        torch.cuda.empty_cache()
+        result["gpu_reference"] = gpu_reference_block(dev, lr, B, T)
+        if "frames_per_sec" in result["gpu_reference"]:
+            result["gpu_reference"]["ours_over_reference"] = round(value / result["gpu_reference"]["frames_per_sec"], 2)
+    if rank == 0 and world == 1 and not args.no_decode:
+        result["decode"] = decode_bench(model, dev, peaks, batches=(1, 2, 4, 8, 16, 32, 64, 128, 256))
     if rank == 0:
         print(json.dumps(result), flush=True)
     if world > 1:
-        # Tear-down: a CUDA graph that captured NCCL kernels keeps the communicator busy and
-        # destroy_process_group() was observed to hang behind it.  Synchronise, meet at a barrier, drop the graph and
-        # leave without the collective destructor (the line above is already flushed).
+        # Tear-down.  Graphs that captured NCCL kernels must be destroyed before the communicator: release them, drain the
+        # device, meet at a barrier, then destroy the process group — on a watchdog, because destroy_process_group() was
+        # observed (round 1) to hang behind captured NCCL nodes; if it has not returned after 30 s the process leaves
+        # without the collective destructor (the result line above is already flushed).
+        import threading
+        train_step.graph = None
         torch.cuda.synchronize()
         dist.barrier()
-        train_step.graph = None
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        done = threading.Event()
+
+        def _destroy():
+            try:
+                dist.destroy_process_group()
+            finally:
+                done.set()
+
+        threading.Thread(target=_destroy, daemon=True).start()
+        if not done.wait(30.0):
+            print(f"rank {rank}: destroy_process_group() still blocked after 30 s, exiting without it", file=sys.stderr, flush=True)
+            os._exit(0)
 
 
 def decode_bench(model, dev, peaks, batches=(1, 64, 256), prompt=150, gen=500, ddim=True):
@@ -326,7 +392,73 @@ def ddim_bench(model, dev, B=16, T=650, steps=100, eta=0.5):
             "ddim_steps": steps, "mode": "whole DDIM loop replayed from one CUDA graph"}
 
 
-# ====================================================================================== CPU baseline / reference arm
+# ====================================================================================== reference arms
+# The UNMODIFIED reference modules (vendored by __graft_entry__.build() into the git-ignored baseline/_ref, which travels to
+# the GPU box) when present; otherwise the oracle port (oracle/lvtr_oracle.py — same arithmetic, proven against the real
+# reference by tests/test_oracle_golden.py).  Used for: `--impl reference` (host cores), `cpu_baseline` (host cores, bounded
+# sample) and `gpu_reference` (the same modules under torch.autocast(bf16) on the same B200 — the stock-PyTorch bar).
+def _reference_modules():
+    try:
+        from baseline import vendor_reference as V
+        if V.available():
+            return V.load()
+    except Exception as e:                                   # noqa: BLE001
+        print("reference modules unavailable:", repr(e), file=sys.stderr)
+    return None
+
+
+class _ReferenceStep:
+    """one training step (fwd + loss assembly of trainers/speech/lvtr.py:103-131 + bwd + AdamW) of the reference model"""
+
+    def __init__(self, device, T, lr, autocast):
+        mods = _reference_modules()
+        self.device, self.autocast = torch.device(device), autocast
+        torch.manual_seed(0)
+        if mods is not None:
+            LVTR, Hparams, TensorMask, masked_loss, cfg = mods
+            hp = Hparams.from_yamlfile(cfg)
+            if T > hp.model.transformer.rpe.maxpos:           # the reference's dense ALiBi buffer (position/alibi.py:8-17)
+                hp.model.transformer.rpe.maxpos = (T + 63) // 64 * 64
+            self.model = LVTR(hp.model, input_dim=N_MELS)
+
+            def init(m):                                      # BaseTrainer.init_weights (training_lib/trainer.py:113-125)
+                if getattr(m, "bias", None) is not None:
+                    m.bias.data.zero_()
+                if callable(getattr(m, "custom_weight_init", None)):
+                    m.custom_weight_init(1.0)
+            self.model.apply(init)
+            self.model.to(self.device)
+            self.TM, self.masked_loss, self.kind = TensorMask, masked_loss, "reference"
+            params = list(self.model.parameters())
+        else:
+            from vae_gslm_b200.hparams.hp import Hparams
+            hp = Hparams.from_yamlfile(CFG)
+            self.sd = {k: v.to(self.device) for k, v in _oracle_state(None, hp).items()}
+            self.sd = {k: v.detach().requires_grad_(v.requires_grad) for k, v in self.sd.items()}
+            self.cfg, self.kind = hp.model.to_dict(), "port"
+            params = [v for v in self.sd.values() if v.requires_grad]
+        self.opt = torch.optim.AdamW([{"params": [p for p in params if p.ndim != 1]},
+                                      {"params": [p for p in params if p.ndim == 1], "weight_decay": 0.0}],
+                                     lr=lr, betas=(0.9, 0.98), weight_decay=0.1,
+                                     **({"fused": True} if self.device.type == "cuda" else {}))
+
+    def __call__(self, batch, rng=None):
+        ctx = torch.autocast(self.device.type, dtype=torch.bfloat16) if self.autocast else torch.autocast(self.device.type, enabled=False)
+        with ctx:
+            if self.kind == "reference":
+                out = self.model(self.TM(batch["x"], batch["mask"]), utterance=self.TM(batch["utterance"], batch["utt_mask"]))
+                kld = self.masked_loss(out["log_q"] * 1.0, out["log_p"], fn=lambda a, b: (a - b))
+                loss = out["decoder_output"] * 1.0 + kld * KW + out["ce_loss"] * 0.5 * KW
+            else:
+                from oracle import lvtr_oracle as O
+                out = O.lvtr_forward(self.sd, self.cfg, batch["x"], batch["mask"], batch["utterance"], batch["utt_mask"], rng)
+                loss = O.total_loss(out, KW)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+
 def _oracle_state(model_or_none, hp):
     from vae_gslm_b200.models.speech.lvtr import LVTR
     from vae_gslm_b200.training_lib.trainer import init_weights
@@ -338,18 +470,6 @@ def _oracle_state(model_or_none, hp):
     return {k: v.detach().float().cpu().clone().requires_grad_(k in names) for k, v in model_or_none.state_dict().items()}
 
 
-def _oracle_step(sd, cfg, batch, rng, opt=None):
-    from oracle import lvtr_oracle as O
-    out = O.lvtr_forward(sd, cfg, batch["x"], batch["mask"], batch["utterance"], batch["utt_mask"], rng)
-    loss = O.total_loss(out, KW)
-    for v in sd.values():
-        v.grad = None
-    loss.backward()
-    if opt is not None:
-        opt.step()
-    return float(loss.detach())
-
-
 def _rng(B, T, seed=4321):
     g = torch.Generator().manual_seed(seed)
     return {"eps_q": torch.randn(B, T, 4, generator=g), "init_state": torch.rand(B, 1, 64, generator=g) * 2 - 1,
@@ -357,19 +477,52 @@ def _rng(B, T, seed=4321):
             "diff_noise": torch.randn(B, T, N_MELS, generator=g)}
 
 
-def cpu_baseline_sample(model, hp, B=2, T=1000):
-    """the oracle (reference algorithm, plain torch fp32) on the box's host cores, one bounded sample."""
+def cpu_baseline_sample(lr, B=2, T=1000):
+    """the reference on the box's host cores (all of them), fp32: one warm-up step and one timed step of a bounded sample
+    (B=2 of the 8 sequences of the workload)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = _oracle_state(model, hp)
-    cfg = hp.model.to_dict()
-    _oracle_step(sd, cfg, synthetic_batch(1, 64, 0), _rng(1, 64))          # warm-up (allocator, thread pools)
+    step = _ReferenceStep("cpu", T, lr, autocast=False)
     batch, rng = synthetic_batch(B, T, 0), _rng(B, T)
+    step(batch, rng)                                          # warm-up at the timed shape (allocator, thread pools, oneDNN)
     t0 = time.perf_counter()
-    _oracle_step(sd, cfg, batch, rng)
+    step(batch, rng)
     dt = time.perf_counter() - t0
-    return {"value": round(B * T / dt, 1), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"1 fwd+bwd of the oracle (fp32, torch CPU) at B={B}, T={T}: {dt:.1f} s",
+    return {"value": round(B * T / dt, 1), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": step.kind,
+            "sample": f"1 warm-up + 1 timed fwd+bwd+AdamW step at B={B}, T={T} (fp32, torch CPU): {dt:.1f} s",
             "host_cpus": os.cpu_count()}
+
+
+def gpu_reference_block(dev, lr, B, T, steps=5, warmup=2):
+    """the stock-PyTorch bar: the reference's own modules — dense-mask SDPA, cuBLAS, cuDNN,
+    ~40 small kernels per layer — under torch.autocast(bf16) with TF32 matmuls (scripts/train.py:44) and fused AdamW, on
+    the SAME B200 and the same synthetic batch, timed with CUDA events.  Its RNG draws are its own (the timing does not
+    depend on them)."""
+    saved = torch.get_float32_matmul_precision()
+    try:
+        torch.set_float32_matmul_precision("high")
+        step = _ReferenceStep(dev, T, lr, autocast=True)
+        batch = {k: v.to(dev) for k, v in synthetic_batch(B, T, 0).items()}
+        rng = {k: v.to(dev) for k, v in _rng(B, T).items()}
+        for _ in range(warmup):
+            step(batch, rng)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step(batch, rng)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = {"frames_per_sec": round(B * T / (ms / 1e3), 1), "ms_per_step": round(ms, 2), "kind": step.kind,
+               "precision": "torch.autocast(bf16) + TF32 matmul, fused AdamW", "batch": B, "frames": T, "steps": steps,
+               "loss": float(loss), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    except Exception as e:                                   # noqa: BLE001
+        out = {"unavailable": repr(e)[:300]}
+    finally:
+        torch.set_float32_matmul_precision(saved)
+    del step
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):
@@ -379,29 +532,25 @@ def run_reference(args):
     from vae_gslm_b200.hparams.hp import Hparams
     torch.set_num_threads(os.cpu_count() or 1)
     hp = Hparams.from_yamlfile(CFG)
-    sd = _oracle_state(None, hp)
-    cfg = hp.model.to_dict()
     B, T = 1, args.frames                                  # bounded sample of the workload per step
-    params = [v for v in sd.values() if v.requires_grad]
-    opt = torch.optim.AdamW([{"params": [p for p in params if p.ndim != 1]},
-                             {"params": [p for p in params if p.ndim == 1], "weight_decay": 0.0}],
-                            lr=hp.training.optimizer.lr, betas=(0.9, 0.98), weight_decay=0.1)
+    step = _ReferenceStep("cpu", T, hp.training.optimizer.lr, autocast=False)
     batch, rng = synthetic_batch(B, T, 0), _rng(B, T)
     for _ in range(args.warmup):
-        _oracle_step(sd, cfg, batch, rng, opt)
+        step(batch, rng)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        loss = _oracle_step(sd, cfg, batch, rng, opt)
+        loss = float(step(batch, rng))
     dt = time.perf_counter() - t0
     value = B * T * args.steps / dt
+    what = ("the UNMODIFIED reference modules (baseline/_ref: models/speech/lvtr.py:143-225, trainers/speech/lvtr.py:103-131)"
+            if step.kind == "reference" else "oracle port of the PyTorch modules")
     print(json.dumps({
         "impl": "reference", "metric": "train_mel_frames_per_sec", "value": round(value, 1), "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"VAE-GSLM training step (fwd+bwd+AdamW), {T / 50:.0f} s segments — reference algorithm "
-                               "(oracle port of the PyTorch modules) on host cores", "per_step_sample": f"B={B}, T={T}",
-                   "frames_per_seq": T, "parallelism": "cpu"},
-        "cpu_baseline": {"value": round(value, 1), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+        "config": {"workload": f"VAE-GSLM training step (fwd+bwd+AdamW), {T / 50:.0f} s segments — {what} on host cores",
+                   "per_step_sample": f"B={B}, T={T}", "frames_per_seq": T, "parallelism": "cpu"},
+        "cpu_baseline": {"value": round(value, 1), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": step.kind,
                          "sample": f"{args.steps} steps of B={B}, T={T} (fwd+bwd+AdamW), fp32"},
         "e2e": {"value": round(value, 1), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "loss": loss}), flush=True)
@@ -417,6 +566,8 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="frames per sequence (20 s segments at 50 Hz)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the B=8,T=640 and B=2,T=3000 steps")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the stock-PyTorch bf16 step on the same GPU")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the training step eagerly (launch-bound)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -229,7 +229,7 @@ class ParamArena:
         bc2 = 1.0 - beta2 ** self.step_count
         k = self.step_count % self._HYPER_DEPTH
         ev = self._hyper_events[k]
-        if ev is not None:
+        if ev is not None and not _capturing():   # (a capture only advances the host counter; nothing reads the ring)
             ev.synchronize()                      # the upload that last read this ring entry has executed
         self._hyper_host = self._hyper_ring[k]
         for grp, host in zip(self.groups, self._hyper_host):

@@ -94,6 +94,8 @@ class TrainStep:
     snapshotted before and restored after, so a fresh or just-resumed model is left exactly as it was found.
     """
 
+    _streams: Dict[tuple, "torch.cuda.Stream"] = {}
+
     def __init__(self, model, arena, reducer, example_batch: Dict[str, torch.Tensor], *, lr: float,
                  kld_weight: float = 0.04, betas=(0.9, 0.98), eps: float = 1e-8, use_cuda_graph: bool = True,
                  warmup_iters: int = 3, overlap_grads: bool = True, accumulate: int = 1,
@@ -122,8 +124,12 @@ class TrainStep:
         # Every execution of the step body — warm-up, capture, eager — runs on ONE private stream.  autograd's
         # AccumulateGrad nodes remember the stream they were first used on (our parameters keep them alive through
         # the pre-assigned arena .grad views and the reducer hooks); if that were the default stream, capture on
-        # another stream would be invalidated.
-        self.stream = torch.cuda.Stream(device=dev)
+        # another stream would be invalidated.  For the same reason every TrainStep of a process (bench.py builds one per
+        # input shape on the same model) shares the stream of the first one.
+        key = (dev.type, dev.index)
+        if key not in TrainStep._streams:
+            TrainStep._streams[key] = torch.cuda.Stream(device=dev)
+        self.stream = TrainStep._streams[key]
         from ... import _lib
         snap = arena.snapshot() if (preserve_state and hasattr(arena, "snapshot")) else None
         n0 = _lib.launch_count
@@ -166,7 +172,13 @@ class TrainStep:
     def _body(self, device_hyper: bool) -> None:
         from ... import ops
         if self.grad_stream is None and self.loss.is_cuda and self.overlap_grads:
-            self.grad_stream = torch.cuda.Stream(device=self.loss.device)
+            # one parameter-gradient stream per process and device: the reducer keeps every side stream it has seen in
+            # `extra_streams` and waits for all of them — a stream left over from an earlier TrainStep would be waited
+            # for from inside a later capture and invalidate it
+            key = ("grad", self.loss.device.index)
+            if key not in TrainStep._streams:
+                TrainStep._streams[key] = torch.cuda.Stream(device=self.loss.device)
+            self.grad_stream = TrainStep._streams[key]
         for side in (self.model.__dict__.get("_side_stream"), self.grad_stream):
             if side is not None and side not in self.reducer.extra_streams:
                 self.reducer.extra_streams.append(side)
