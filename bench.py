@@ -203,8 +203,18 @@ def run_ours(args):
         torch.cuda._sleep(1000)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
-    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in prof)
-    gemm_flops = sum(f for _, _, f, _ in prof)
+    gemm_ms = sum(p_[0].elapsed_time(p_[1]) for p_ in prof)
+    gemm_flops = sum(p_[2] for p_ in prof)
+    if os.environ.get("VG_BENCH_GEMM_TABLE") == "1" and rank == 0:
+        agg = {}
+        for p_ in prof:
+            a_ = agg.setdefault(p_[4], [0, 0.0, 0.0])
+            a_[0] += 1
+            a_[1] += p_[0].elapsed_time(p_[1])
+            a_[2] += p_[2]
+        print("| M | N | K | tA | tB | out | act | bias | launches | ms | TFLOP/s |\n|---|---|---|---|---|---|---|---|---:|---:|---:|", file=sys.stderr)
+        for k_, (n_, ms_, fl_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print("| " + " | ".join(str(x) for x in k_) + f" | {n_} | {ms_:.3f} | {fl_ / ms_ / 1e9:.0f} |", file=sys.stderr)
     peaks = measured_peaks()
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     step_ms = ms / args.steps

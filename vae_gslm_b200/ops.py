@@ -127,7 +127,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
     L.call("vg_gemm", C.byref(g), be, None, 0, L.stream())
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K, a.dtype))
+        prof.append((e0, e1, 2.0 * M * N * K, a.dtype, (M, N, K, int(trans_a), int(trans_b), str(out.dtype)[6:], act, bias is not None)))
     return out
 
 
