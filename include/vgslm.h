@@ -96,6 +96,13 @@ int    vg_gemm(const vg_gemm_args* a, int backend, void* workspace, size_t works
 /* SMs the persistent tcgen05 GEMM grids may occupy (default 148 = all; env VG_GEMM_SMS).  Data-parallel training leaves
  * a few SMs to the NCCL all-reduce kernels that overlap backward (scripts/train.py:93-95 → DDP). */
 int    vg_set_gemm_sm_budget(int sms);
+/* Programmatic dependent launch for chains of short kernels (the layer-by-layer cached generation step, LVTR.step at
+ * batch >= 64: ~7 launches per layer of lvtr.py:253-257 / transformer/layers.py:134-195).  bit 0: vg_gemm (tcgen05
+ * path) and vg_rmsnorm_fwd are launched with the programmatic-stream-serialization attribute — their prologue (barrier
+ * init, TMEM allocation, tensor-map prefetch) overlaps the tail of the kernel in front and they execute
+ * griddepcontrol.wait before touching memory; bit 1: the B operand of vg_gemm is a static weight and its first ring
+ * stages are fetched BEFORE the wait.  Process-wide; 0 (default) = plain stream order. */
+int    vg_set_pdl_mode(int mode);
 /* column sums: out[n] = beta * out[n] + sum_m X[m,n] (bias gradients), deterministic; beta in {0,1}. */
 size_t vg_colsum_workspace(int64_t rows, int64_t cols);
 int    vg_colsum(const void* x, int64_t ld, float* out, int64_t rows, int64_t cols, int x_dtype, float beta,

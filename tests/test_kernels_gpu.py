@@ -353,6 +353,34 @@ def test_attention_decode_and_cache(dtype):
     assert rel_err(o, ref) < tol(dtype)
 
 
+@pytest.mark.parametrize("B,H,pos,splits", [(5, 16, 333, 1), (40, 16, 401, 1), (3, 16, 650, 7), (1, 16, 64, 2),
+                                            (21, 16, 129, 3), (2, 4, 0, 1), (2, 4, 1, 4)])
+def test_attention_decode_stream_kernel(B, H, pos, splits):
+    """the bf16 product kernel (bulk-TMA ring, persistent CTAs): several ring wraps per item, several items per CTA,
+    ragged last stage, empty trailing splits, the device-resident position, and the in-place append"""
+    D, Tmax = 64, 704
+    C = H * D
+    dt = torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(pos * 131 + B)
+    slopes = torch.tensor(ops.alibi_slopes(H), device=DEV)
+    kv = (0.5 * torch.randn(2, B, H, Tmax, D, generator=g)).to(DEV).to(dt)
+    kc, vc = kv[0].clone(), kv[1].clone()
+    qkv = (0.5 * torch.randn(B, 1, 3 * C, generator=g)).to(DEV).to(dt)
+    tickets = torch.zeros(B * H, dtype=torch.int32, device=DEV)
+    pos_dev = torch.tensor([pos], dtype=torch.int32, device=DEV)
+    o = ops.attention_decode(qkv.view(B, 3 * C), kc, vc, 0, slopes, pos_dev=pos_dev, splits=splits,
+                             tickets=tickets)
+    assert int(tickets.abs().sum()) == 0
+    k_ref = torch.cat([kv[0][:, :, :pos].transpose(1, 2).reshape(B, pos, C), qkv[..., C:2 * C]], 1)
+    v_ref = torch.cat([kv[1][:, :, :pos].transpose(1, 2).reshape(B, pos, C), qkv[..., 2 * C:]], 1)
+    ref = _attn_ref(qkv, H, None, slopes, q_offset=pos, k=k_ref, v=v_ref)
+    assert rel_err(o.view(B, 1, C), ref) < tol(dt)
+    # row pos was appended, nothing else was touched
+    assert torch.equal(kc[:, :, pos].reshape(B, C), qkv[:, 0, C:2 * C]) and torch.equal(vc[:, :, pos].reshape(B, C), qkv[:, 0, 2 * C:])
+    kc[:, :, pos], vc[:, :, pos] = kv[0][:, :, pos], kv[1][:, :, pos]
+    assert torch.equal(kc, kv[0]) and torch.equal(vc, kv[1])
+
+
 # ------------------------------------------------------------------------------------ losses
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_softmax_ce(dtype):

@@ -10,6 +10,9 @@
 namespace vg {
 
 void set_error(const char* fmt, ...);
+// vg_set_pdl_mode (include/vgslm.h): bit 0 = launch vg_gemm / vg_rmsnorm_fwd with the programmatic-dependent-launch
+// attribute, bit 1 = the B operand of vg_gemm is a static weight (prefetched before griddepcontrol.wait)
+extern int g_pdl_mode;
 
 #define VG_REQUIRE(cond, code, ...)                     \
   do {                                                  \

@@ -44,6 +44,7 @@ struct TcEpilogue {
   int vec_ok;    // every pointer/ld allows 8-wide vector access
   int variant;   // TcVariant
   int splits;    // split-K factor (1 = off); >1 requires TCV_RED
+  int pdl;       // vg_set_pdl_mode at launch time (0 = plain stream order)
 };
 
 // ---- warp-private transpose scratch ---------------------------------------------------------------------------
@@ -397,6 +398,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_units = num_m * num_n * epi.splits;
   const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
 
+  // Programmatic dependent launch (vg_set_pdl_mode): everything above overlapped the tail of the kernel in front; the
+  // kernel behind may start its own prologue now.  Every role waits for the predecessor's memory before it touches
+  // global memory — except the producer's prefetch of a STATIC B operand (weights) into the first ring stages.
+  // Both instructions are no-ops in a launch without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  int pdl_prefetched = 0;
+  if (!(warp == 0 && (epi.pdl & 2) && CTAS == 1 && VG_GEMM_UNIFORM_ISSUE != 0)) asm volatile("griddepcontrol.wait;" ::: "memory");
+
   // VG_GEMM_UNIFORM_ISSUE (compile-time, default 1): the producer / MMA-issuer warps walk their loops as whole warps and
   // one elect.sync-elected lane issues.  Inside a `lane == 0` branch the compiler wraps every TMA / tcgen05.mma in a
   // per-thread ELECT / R2UR / BRA.U.ANY loop (~80 cycles per instruction: measured in the attention kernels, where the
@@ -408,15 +417,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer (every CTA loads its own A rows and its own slice of B) =====================
     int s = 0;
     uint32_t ph = 0;
+    if constexpr (CTAS == 1) {
+      if ((epi.pdl & 2) && kUniformIssue) {
+        // static-weight prefetch: B tiles of the first unit's first k-blocks, before the predecessor is done
+        if (unit0 < num_units) {
+          const TcUnit w = tc_unit(unit0, num_m, num_kb, epi.splits, BN, TBM);
+          const int npf = (w.kb1 - w.kb0) < kStages ? (w.kb1 - w.kb0) : kStages;
+          if (elect_one()) {
+            for (int i = 0; i < npf; ++i) {
+              uint8_t* b_dst = smem + i * Cfg::kStageBytes + A_TILE_BYTES;
+              const int k0 = (w.kb0 + i) * TBK;
+              mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
+              if constexpr (!B_MN) {
+                tma_load_2d(b_dst, &tmB, &full_bar[i], k0, w.n0);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BNL / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[i], w.n0 + 64 * j, k0);
+              }
+            }
+          }
+          __syncwarp();
+          pdl_prefetched = npf;
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+      }
+    }
     for (int u = unit0; u < num_units; u += unit_step) {
       const TcUnit w = tc_unit(u, num_m, num_kb, epi.splits, BN, TBM * CTAS);
       const int m0 = w.m0 + cta_rank * TBM;
       const int n0 = w.n0 + cta_rank * BNL;
       for (int kb = w.kb0; kb < w.kb1; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const bool b_done = pdl_prefetched > 0;      // this stage's B tile and expect_tx were issued before the wait
+        if (b_done) --pdl_prefetched;
+        else mbar_wait(&empty_bar[s], ph ^ 1u);
         uint8_t* a_dst = smem + s * Cfg::kStageBytes;
         uint8_t* b_dst = a_dst + A_TILE_BYTES;
         const int k0 = kb * TBK;
+        if (b_done) {
+          if (elect_one()) {
+            if constexpr (!A_MN) {
+              tma_load_2d(a_dst, &tmA, &full_bar[s], k0, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < TBM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full_bar[s], m0 + 64 * j, k0);
+            }
+          }
+        } else
         if (!kUniformIssue || elect_one()) {
         if constexpr (CTAS == 2) {
           // both CTAs' bytes are counted on the LEADER's barrier (the MMA issuer lives there)
@@ -550,13 +596,23 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const vg_ge
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CTAS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CTAS == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CTAS;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  epi.pdl = g_pdl_mode;
+  if (epi.pdl & 1) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CTAS == 2 ? 1 : 0;
+  cfg.numAttrs = na;
   VG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, (int)a->M, (int)a->N, (int)a->K, epi));
   return 0;
 }

@@ -20,6 +20,10 @@ rmsnorm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ scale,
                    int64_t rows, int dim, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kRmsWarps + (threadIdx.x >> 5);
+  // programmatic dependent launch (vg_set_pdl_mode; no-ops otherwise): the kernel behind may start its prologue, and x
+  // is complete once the kernel in front is
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (row >= rows) return;
   const TX* xr = x + row * dim;
   Vec8<TX> v[ITERS];
@@ -158,9 +162,18 @@ static int launch_fwd(const void* x, const float* scale, const uint8_t* mask, vo
                       int64_t rows, int dim, float eps, cudaStream_t st) {
   const int iters = (dim + 255) / 256;
   dim3 grid((unsigned)ceil_div(rows, kRmsWarps)), block(kRmsWarps * 32);
-#define VG_RMS_FWD(I)                                                                          \
-  rmsnorm_fwd_kernel<TX, TY, I><<<grid, block, 0, st>>>((const TX*)x, scale, mask, (TY*)y, rstd, \
-                                                        rows, dim, eps)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (g_pdl_mode & 1) ? 1 : 0;
+#define VG_RMS_FWD(I)                                                                                        \
+  VG_CUDA(cudaLaunchKernelEx(&cfg, rmsnorm_fwd_kernel<TX, TY, I>, (const TX*)x, scale, mask, (TY*)y, rstd, \
+                             rows, dim, eps))
   if (iters <= 1) VG_RMS_FWD(1);
   else if (iters <= 2) VG_RMS_FWD(2);
   else if (iters <= 4) VG_RMS_FWD(4);

@@ -16,6 +16,8 @@ Additive API: the five RNG draws of the reference forward can be i
 """
 from __future__ import annotations
 
+import os
+
 import contextlib
 import math
 from typing import List, Mapping, Optional, Tuple
@@ -97,6 +99,7 @@ class LVTR(nn.Module):
         self.compute_dtype = torch.float32
         self.overlap_decoder = True         # diffusion decoder branch on a side stream (parallel graph branch)
         self.use_decode_engine = True       # bf16 single-frame steps run on decode.DecodeEngine ...
+        self.decode_pdl = os.environ.get("VG_DECODE_PDL", "1") != "0"     # layer-by-layer cached step as a PDL chain
         # ... up to this batch: measured on B200 (profiles/r01_decode.md) the weight-streaming engine wins up to ~100
         # sequences (0.47 vs 1.21 ms per step at B=1, 1.02 vs 1.37 at 64), the tcgen05 layer-by-layer path above
         self.decode_engine_max_batch = 96
@@ -302,14 +305,19 @@ class LVTR(nn.Module):
             head, logits = head2.view(u.shape[0], 1, -1), logits2.view(u.shape[0], 1, -1)
             outputs = {"transformer_latent": TensorMask(H), "kv": past_kv}
         else:
-            z_given = stack.run(TensorMask(u), memory=c, past_kv=past_kv, return_attn=return_attn, return_kv=True)
+            # a single cached frame in bf16 is ~120 short launches (7 per layer): run them as a programmatic-dependent-
+            # launch chain with the weights prefetched ahead of each dependency wait (ops.pdl_mode)
+            chain = (u.shape[1] == 1 and past_kv is not None and u.is_cuda and self.compute_dtype == torch.bfloat16
+                     and not torch.is_grad_enabled() and self.decode_pdl)
+            with ops.pdl_mode(3 if chain else 0):
+                z_given = stack.run(TensorMask(u), memory=c, past_kv=past_kv, return_attn=return_attn, return_kv=True)
+                H = z_given["output"].value
+                c_lat, head, logits = self._post_stack(H)
             outputs = {"transformer_latent": z_given["output"], "kv": z_given["kv"]}
             if return_distrbution:
                 outputs["z_given"] = z_given
             if return_attn:
                 outputs["self_attn"] = z_given["self_attn"]
-            H = z_given["output"].value
-            c_lat, head, logits = self._post_stack(H)
         Bq, Tq, _ = H.shape
         Ld = self.hp.latent_dim
         if eps is None:

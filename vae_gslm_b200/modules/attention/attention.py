@@ -109,7 +109,8 @@ class SelfAttention(nn.Module):
         pos = cache.length
         assert pos + Tq <= cache.max_len, "KV cache too small (TransformerLayerStack.run grows it before the loop)"
         if Tq == 1:
-            o = ops.attention_decode(qkv.view(B, C3), cache.k(li), cache.v(li), pos, slopes, cache.pos_dev, scale)
+            o = ops.attention_decode(qkv.view(B, C3), cache.k(li), cache.v(li), pos, slopes, cache.pos_dev, scale,
+                                     tickets=cache.tickets)
             o = o.view(B, 1, C)
         else:
             ops.kv_append(k, v, cache.k(li), cache.v(li), pos)

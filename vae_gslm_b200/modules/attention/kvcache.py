@@ -21,6 +21,8 @@ class KVCache:
         self.buf = torch.empty((n_layers, 2, batch, nheads, self.max_len, head_dim), dtype=dtype, device=device)
         self.length = 0                       # host-side number of valid positions (same for all layers)
         self.pos_dev: Optional[torch.Tensor] = None   # optional device-resident copy for CUDA-graph replay
+        # split-KV decode: per-(sequence, head) arrival counters, zero between launches (vg_attn_decode merges in-kernel)
+        self.tickets = torch.zeros(batch * nheads, dtype=torch.int32, device=device)
 
     def k(self, layer: int) -> torch.Tensor:
         return self.buf[layer, 0]

@@ -545,6 +545,38 @@ def kv_append(k: torch.Tensor, v: torch.Tensor, k_cache: torch.Tensor, v_cache: 
            L.dtype_id(k.dtype), L.stream())
 
 
+class pdl_mode:
+    """``with ops.pdl_mode(3):`` — vg_gemm / vg_rmsnorm_fwd launched inside run as a programmatic-dependent-launch chain
+    (include/vgslm.h ``vg_set_pdl_mode``): bit 0 overlaps each kernel's prologue with the tail of the one in front, bit 1
+    additionally declares every GEMM B operand a static weight (prefetched before the dependency wait).  For inference
+    chains of short kernels only (the layer-by-layer cached generation step); process-wide, restored on exit."""
+    _current = 0
+
+    def __init__(self, mode: int) -> None:
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = pdl_mode._current
+        L.call("vg_set_pdl_mode", self.mode)
+        pdl_mode._current = self.mode
+        return self
+
+    def __exit__(self, *exc):
+        L.call("vg_set_pdl_mode", self.prev)
+        pdl_mode._current = self.prev
+        return False
+
+
+def decode_splits(n_bh: int, horizon: int, slots: int = 3 * 148) -> int:
+    """kv-splits per (sequence, head) for ``vg_attn_decode``.  Its persistent CTAs (3 per SM) each take a contiguous run of
+    (b, h, split) items; a split costs a partial write, a ticket and a merge by the last arriver (~3 us per item on the
+    critical path of a CTA, profiles/r02_decode.md), which is more than the imbalance it removes at every cache length of
+    the generation recipe (<= 650 keys) — so splits are only used when a handful of long items would leave the GPU idle."""
+    if n_bh >= slots // 2 or horizon <= 1024:
+        return 1
+    return max(1, min(16, slots // n_bh, horizon // 512))
+
+
 @torch.no_grad()
 def attention_decode(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, pos: int,
                      slopes: Optional[torch.Tensor], pos_dev: Optional[torch.Tensor] = None,
@@ -554,10 +586,9 @@ def attention_decode(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Te
     B, C3 = qkv.shape
     _, H, Tmax, D = k_cache.shape
     scale = scale if scale is not None else 1.0 / math.sqrt(D)
-    if splits is None:      # fill ~2 waves of 148 SMs when the batch alone cannot; with a device-resident position
-        # (CUDA-graph replay) the split count is frozen at capture time, so size it for the whole cache
-        horizon = Tmax if pos_dev is not None else pos + 1
-        splits = max(1, min(16, (2 * 148 + B * H - 1) // (B * H), (horizon + 63) // 64))
+    if splits is None:      # with a device-resident position (CUDA-graph replay) the split count is frozen at capture
+        # time, so size it for the whole cache
+        splits = decode_splits(B * H, Tmax if pos_dev is not None else pos + 1)
     if out is None:
         out = torch.empty((B, C3 // 3), dtype=qkv.dtype, device=qkv.device)
     assert out.shape == (B, C3 // 3) and out.is_contiguous() and out.dtype == qkv.dtype
