@@ -348,6 +348,16 @@ int vg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vg_stream_t stre
  * big matrices are overwritten by their first weight-gradient GEMM of the step (beta = 0) instead. */
 int vg_zero_segments(float* base, const int64_t* seg_off, const int64_t* seg_len, int n_seg, vg_stream_t stream);
 
+/* ---- strided Conv1d of the utterance encoder as a GEMM on [B,T,C] rows (modules/conv/layers.py:549-593 ConvNormAct,
+ * models/speech/lvtr.py:127-136,203-207): the window gather in front of vg_gemm and its adjoint.
+ *   a[b, t, c*K + j] = f(x[b, S*t - pad + j, c])  (0 outside [0,T)),  T_out = (T + 2 pad - K) / S + 1,  f = ReLU if relu
+ * Column order = memory order of the Conv1d weight [Cout, Cin, K]: the convolution is one GEMM with the weight in place.
+ * bwd: dx = adjoint(da), multiplied by [x_relu > 0] when x_relu (the forward input of a relu gather) is given.          */
+int vg_im2col_fwd(const void* x, void* a, int64_t B, int64_t T, int64_t C, int64_t K, int64_t S, int64_t pad,
+                  int64_t T_out, int relu, int dtype, vg_stream_t stream);
+int vg_im2col_bwd(const void* da, const void* x_relu /* nullable */, void* dx, int64_t B, int64_t T, int64_t C, int64_t K,
+                  int64_t S, int64_t pad, int64_t T_out, int dtype, vg_stream_t stream);
+
 /* ---- persistent cached-generation step: the transformer part of LVTR.step (models/speech/lvtr.py:253-279 →
  * modules/transformer/layers.py:134-195 with past_kv, modules/attention/attention.py:52-85, modules/norm.py:28-32,
  * lvtr.py:171,172,194,195) as ONE cooperative launch — stack-input linear, L x [RMSNorm1+QKV | cached attention + KV append |

@@ -381,6 +381,33 @@ def test_attention_decode_stream_kernel(B, H, pos, splits):
     assert torch.equal(kc, kv[0]) and torch.equal(vc, kv[1])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,Cin,Cout,K,S,pad,relu", [(3, 150, 64, 128, 4, 2, 1, False), (2, 75, 128, 256, 4, 2, 1, True),
+                                                       (2, 37, 256, 512, 4, 2, 1, True), (2, 18, 64, 64, 1, 1, 0, True),
+                                                       (2, 21, 16, 24, 3, 1, 1, False), (1, 9, 8, 8, 5, 3, 2, True)])
+def test_strided_conv_as_gather_plus_gemm(dtype, B, T, Cin, Cout, K, S, pad, relu):
+    """ops.im2col + ops.linear with the Conv1d weight in place == F.conv1d on B,C,T (forward, dx, dW, db), including the
+    ReLU-on-read of the previous layer (conv/layers.py:549-593)"""
+    x = torch.randn(B, T, Cin, device=DEV).to(dtype).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, K, device=DEV) / (Cin * K) ** 0.5).requires_grad_(True)
+    b = (0.1 * torch.randn(Cout, device=DEV)).requires_grad_(True)
+    a = ops.im2col(x, K, S, pad, relu=relu)
+    y = ops.linear(a, w, b)
+    go = torch.randn_like(y)
+    y.backward(go)
+    xr = x.detach().float().requires_grad_(True)
+    wr, br = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    wq = wr.to(dtype).float() if dtype == torch.bfloat16 else wr
+    yr = torch.nn.functional.conv1d((torch.relu(xr) if relu else xr).transpose(1, 2), wq, br, stride=S, padding=pad).transpose(1, 2)
+    assert y.shape == yr.shape
+    yr.backward(go.float())
+    t = tol(dtype)
+    assert rel_err(y, yr) < t
+    assert rel_err(x.grad, xr.grad) < t and rel_err(w.grad, wr.grad) < t and rel_err(b.grad, br.grad) < t
+    if relu:
+        assert torch.equal(x.grad == 0, (x.detach() <= 0) | (x.grad == 0))       # the ReLU mask is applied in the adjoint
+
+
 # ------------------------------------------------------------------------------------ losses
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_softmax_ce(dtype):

@@ -613,3 +613,53 @@ def test_eval_after_training_sees_the_updated_weights(golden):
                    init_state=d["init_state"].to(DEV))
     l2 = fresh.step(o["output"][:, -1:], past_kv=o["kv"], temperature=0.0, greedy=True, return_logits=True)["logits"].float().cpu()
     assert max_rel(l1, l2) < 2e-2
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_utterance_encoder_rows_path_matches_conv1d_path(dtype, tol):
+    """the full-size utterance encoder (Linear → 3 x [Conv1d k4 s2 → channel norm → ReLU] → Linear →
+    masked time mean; models/speech/lvtr.py:127-136, conv/layers.py:549-642) on the libvgslm route (window gather +
+    GEMM + row norm, [B,T,C] throughout) against the nn.Conv1d route of the same modules (B,C,T, cuDNN) on the same
+    weights: embedding, input gradient and every parameter gradient; ragged utterance lengths (the reference's growing
+    length makes every down-sampled frame valid, so only the first linear sees the padding)."""
+    from vae_gslm_b200.modules.conv.layers import CNNStack
+    from vae_gslm_b200.modules.linear.layers import TimeAggregation
+    hp = Hparams.from_yamlfile(os.path.join(ROOT, "vae_gslm_b200", "configs", "train", "speech", "vae-gslm.yaml"))
+    torch.manual_seed(5)
+    stack = CNNStack(hp.model.utterance_encoder, input_dim=80, output_dim=hp.model.utterance_encoder.embedding_dim).to(DEV)
+    with torch.no_grad():
+        for n, p in stack.named_parameters():
+            if n.endswith("bias") or "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    agg = TimeAggregation()
+    B, T = 5, 150
+    x = torch.randn(B, T, 80, device=DEV)
+    length = torch.tensor([150, 97, 150, 31, 120], device=DEV)
+    mask = torch.arange(T, device=DEV)[None] < length[:, None]
+    go = torch.randn(B, hp.model.utterance_encoder.embedding_dim, device=DEV)
+
+    def run(rows, autocast=False):
+        stack.zero_grad(set_to_none=True)
+        stack.compute_dtype = dtype if rows else torch.float32
+        xi = x.clone().requires_grad_(True)
+        stack._rows_path = (lambda t: True) if rows else (lambda t: False)
+        assert CNNStack._rows_path(stack, TensorMask(xi, mask))          # the shipped configuration takes the new route
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            u = agg(stack(TensorMask(xi, mask))).float()
+        u.backward(go)
+        return u.detach(), xi.grad, {n: p.grad.clone() for n, p in stack.named_parameters()}
+
+    u1, dx1, g1 = run(True)
+    u0, dx0, g0 = run(False)
+    if dtype == torch.float32:                      # the same arithmetic
+        assert max_rel(u1, u0) < tol and max_rel(dx1, dx0) < tol
+        for n in g0:
+            assert frob_rel(g1[n], g0[n]) < tol, (n, frob_rel(g1[n], g0[n]))
+        return
+    # bf16: the bound of tests/test_parity_full_gpu.py — within 2e-2 of the fp32 route, or within 2.5x of what stock
+    # autocast does to the same quantity (bf16 activations flip single ReLU decisions behind an eps = 1e-6 channel norm)
+    ua, dxa, ga = run(False, autocast=True)
+    assert max_rel(u1, u0) < max(tol, 2.5 * max_rel(ua, u0)), (max_rel(u1, u0), max_rel(ua, u0))
+    assert frob_rel(dx1, dx0) < max(tol, 2.5 * frob_rel(dxa, dx0)), (frob_rel(dx1, dx0), frob_rel(dxa, dx0))
+    for n in g0:
+        assert frob_rel(g1[n], g0[n]) < max(tol, 2.5 * frob_rel(ga[n], g0[n])), (n, frob_rel(g1[n], g0[n]), frob_rel(ga[n], g0[n]))

@@ -120,6 +120,8 @@ _SIGNATURES = {
     "vg_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_int, _p, _sz, _p]),
     "vg_set_gemm_sm_budget": (C.c_int, [C.c_int]),
     "vg_set_pdl_mode": (C.c_int, [C.c_int]),
+    "vg_im2col_fwd": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _p]),
+    "vg_im2col_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, C.c_int, _p]),
     "vg_colsum_workspace": (_sz, [_i64, _i64]),
     "vg_colsum": (C.c_int, [_p, _i64, _p, _i64, _i64, C.c_int, _f32, _p, _sz, _p]),
     "vg_mask_rows": (C.c_int, [_p, _p, _p, _i64, _i64, C.c_int, _p]),

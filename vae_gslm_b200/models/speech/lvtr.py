@@ -117,7 +117,10 @@ class LVTR(nn.Module):
         assert dtype in (torch.float32, torch.bfloat16)
         self.compute_dtype = dtype
         self.transformer[0].compute_dtype = dtype
-        for net in (self.encoder[0], self.decoder.model.unet):          # conv stacks on libvgslm (B,T,C layout)
+        nets = [self.encoder[0], self.decoder.model.unet]                 # conv stacks on libvgslm (B,T,C layout)
+        if self.utterance_encoder is not None:
+            nets.append(self.utterance_encoder[0])
+        for net in nets:
             if hasattr(net, "compute_dtype"):
                 net.compute_dtype = dtype
         return self

@@ -259,8 +259,21 @@ class CNNStack(nn.Module):
         self.layers = nn.ModuleList(layers)
         self.linear = nn.Linear(input_dim, hp.init_channel) if input_dim is not None else None
         self.out_linear = nn.Linear(hp.out_channels[-1], output_dim) if output_dim is not None else None
+        self.compute_dtype = torch.float32          # set by LVTR.set_compute_dtype
+
+    def _rows_path(self, x: TensorMask) -> bool:
+        """the libvgslm route: strided Conv1d → channel norm → ReLU layers on a CUDA [B,T,C] tensor"""
+        from ..norm import InstanceNorm
+        return (x.value.is_cuda and self.linear is not None and self.out_linear is not None
+                and all(isinstance(l.norm, InstanceNorm) and isinstance(l.act, nn.ReLU) and l.stride != 1
+                        and l.conv.two_side_padding is None and l.conv.dilation[0] == 1 and l.conv.groups == 1
+                        and l.conv.out_channels >= 16 and l.conv.out_channels % 8 == 0       # the row-norm kernel's range
+                        and (l.conv.in_channels * l.conv.kernel_size[0]) % 8 == 0
+                        for l in self.layers))
 
     def forward(self, x: TensorMask) -> TensorMask:
+        if self._rows_path(x):
+            return self._forward_rows(x)
         if self.linear is not None:
             x = TensorMask(self.linear(x.value), x.mask).apply_mask()
         x = x.transpose()
@@ -270,6 +283,27 @@ class CNNStack(nn.Module):
         if self.out_linear is not None:
             x = TensorMask(self.out_linear(x.value), x.mask).apply_mask()
         return x.apply_mask()
+
+    def _forward_rows(self, x: TensorMask) -> TensorMask:
+        """Same arithmetic as above without leaving the [B,T,C] layout (reference: conv/layers.py:549-593,631-642): every
+        strided convolution is a window gather (ops.im2col, which also applies the previous layer's ReLU on read) plus ONE
+        tcgen05 GEMM with the Conv1d weight used in place, the channel norm is the fused row kernel of the encoder
+        (ops.dwconv_ln without its convolution), and nothing runs on cuDNN.  The recorded length GROWS by the stride per
+        layer exactly as in the reference (ConvNormAct quirk), so every down-sampled frame is valid."""
+        h = ops.linear(x.value.to(self.compute_dtype), self.linear.weight, self.linear.bias, row_mask=x.mask)
+        length = x.length
+        relu = False
+        for layer in self.layers:
+            conv = layer.conv
+            a = ops.im2col(h, conv.kernel_size[0], conv.stride[0], conv.padding[0], relu=relu)
+            y = ops.linear(a, conv.weight, conv.bias)
+            h = ops.dwconv_ln(y, None, None, None, layer.norm.weight, layer.norm.bias, 0, layer.norm.eps)
+            relu = True
+            length = TensorMask.resize_length(length, 1.0 / float(layer.stride))
+        h = ops.im2col(h, 1, 1, 0, relu=True)
+        out = TensorMask.fromlength(h, length, axis=1)
+        y = ops.linear(h, self.out_linear.weight, self.out_linear.bias, row_mask=out.mask)
+        return TensorMask(y, out.mask)
 
     @property
     def sample_ratio(self) -> float:

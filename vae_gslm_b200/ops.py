@@ -454,6 +454,37 @@ def dwconv_ln(x: torch.Tensor, conv_w: Optional[torch.Tensor], conv_b: Optional[
     return _DwConvLN.apply(x, conv_w, conv_b, t_add, ln_w, ln_b, pad_left, eps, out_cols)
 
 
+# ------------------------------------------------------------------ strided Conv1d as a GEMM (utterance encoder)
+class _Im2col(torch.autograd.Function):
+    """a[b,t,c*K+j] = f(x[b, S*t - pad + j, c]) on [B,T,C] rows, f = ReLU (of the previous ConvNormAct) or identity
+    (conv/layers.py:549-593).  The column order is the memory order of the Conv1d weight [Cout,Cin,K]."""
+
+    @staticmethod
+    def forward(ctx, x, K, S, pad, relu):
+        B, T, Cc = x.shape
+        xc = x.contiguous()
+        Tout = (T + 2 * pad - K) // S + 1
+        a = torch.empty((B, Tout, Cc * K), dtype=x.dtype, device=x.device)
+        L.call("vg_im2col_fwd", L.ptr(xc), L.ptr(a), B, T, Cc, K, S, pad, Tout, int(relu), L.dtype_id(x.dtype), L.stream())
+        ctx.save_for_backward(xc if relu else None)
+        ctx.meta = (B, T, Cc, K, S, pad, Tout)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        (xr,) = ctx.saved_tensors
+        B, T, Cc, K, S, pad, Tout = ctx.meta
+        dac = da.contiguous()
+        dx = torch.empty((B, T, Cc), dtype=da.dtype, device=da.device)
+        L.call("vg_im2col_bwd", L.ptr(dac), L.ptr(xr), L.ptr(dx), B, T, Cc, K, S, pad, Tout, L.dtype_id(da.dtype), L.stream())
+        return dx, None, None, None, None
+
+
+def im2col(x: torch.Tensor, kernel_size: int, stride: int, pad: int, relu: bool = False) -> torch.Tensor:
+    """[B,T,C] → [B,T_out,C*K] window gather (optionally of relu(x)); ``im2col(x, 1, 1, 0, relu=True)`` is relu(x)."""
+    return _Im2col.apply(x, int(kernel_size), int(stride), int(pad), bool(relu))
+
+
 # -------------------------------------------------------------------------------------- attention
 def alibi_slopes(nheads: int) -> list:
     """Head slopes of position/alibi.py:19-30 (geometric sequence; interleaved for non powers of two)."""
