@@ -2,6 +2,8 @@
 Tolerances: fp32 kernels 1e-4 relative (north star), bf16 kernels 2e-2."""
 import math
 
+import os
+
 import pytest
 import torch
 
@@ -379,6 +381,19 @@ def test_attention_decode_stream_kernel(B, H, pos, splits):
     assert torch.equal(kc[:, :, pos].reshape(B, C), qkv[:, 0, C:2 * C]) and torch.equal(vc[:, :, pos].reshape(B, C), qkv[:, 0, 2 * C:])
     kc[:, :, pos], vc[:, :, pos] = kv[0][:, :, pos], kv[1][:, :, pos]
     assert torch.equal(kc, kv[0]) and torch.equal(vc, kv[1])
+
+
+@pytest.mark.parametrize("cfg", ["64542", "128382"])
+def test_attention_decode_stream_kernel_other_ring_shapes(cfg):
+    """the two runner-up ring shapes of the sweep (VG_AD_CFG is read once per process: run the test above in a child)"""
+    if os.environ.get("VG_AD_CFG"):
+        pytest.skip("already inside the child process")
+    import subprocess
+    import sys
+    env = dict(os.environ, VG_AD_CFG=cfg)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", __file__, "-k", "test_attention_decode_stream_kernel and not other"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
