@@ -348,6 +348,31 @@ int vg_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vg_stream_t stre
  * big matrices are overwritten by their first weight-gradient GEMM of the step (beta = 0) instead. */
 int vg_zero_segments(float* base, const int64_t* seg_off, const int64_t* seg_len, int n_seg, vg_stream_t stream);
 
+/* ---- skinny linear layer for the cached generation step: y[B,N] = epilogue(x[B,K] · W[N,K]^T), B <= 256 rows — every
+ * nn.Linear that LVTR.step runs on one new frame per sequence (attention.py:52,79, transformer/layers.py:82,152,
+ * lvtr.py:171,172,194,195) when the step runs layer by layer.  Swap-AB tcgen05 GEMM: 128 output features per CTA as the M
+ * operand, the batch as the N operand, the k-range split over a thread-block cluster whose partial tiles are
+ * reduce-scattered through distributed shared memory; weights prefetched ahead of the programmatic-dependent-launch wait.
+ * Epilogue order as vg_gemm: (x row scale 1/rms) → + bias → activation → (row mask if mask_before_residual) → + residual → (row mask otherwise).
+ * x, W bf16 with unit inner stride (ld multiples of 8); y / residual bf16 or f32 (y_dtype); K a multiple of 64.            */
+typedef struct {
+  const void* x; int64_t ldx;
+  const void* w; int64_t ldw;
+  void* y; int64_t ldy;
+  const float* bias;                 /* nullable, [N] */
+  const void* residual; int64_t ld_res;   /* nullable, [B, N] in y_dtype */
+  const uint8_t* row_mask;           /* nullable, [B] */
+  int64_t B, N, K;
+  int32_t y_dtype;                   /* VG_F32 | VG_BF16 */
+  int32_t act;                       /* vg_act: NONE | RELU | GELU | SILU */
+  int32_t mask_before_residual;
+  float ss_inv_k, ss_eps;            /* folded RMSNorm (norm.py:28-32): acc *= rsqrt(row_ss_in[b] * ss_inv_k + ss_eps), the norm's */
+  const float* row_ss_in;            /* scale vector pre-multiplied into W by the caller; nullable                              */
+  float* row_ss_out;                 /* nullable, [B]: += sum over features of the stored y^2 (the next RMSNorm's statistics)    */
+  float* zero_ss;                    /* nullable, [B]: cleared (the accumulator of a later launch)                               */
+} vg_skinny_linear_args;
+int vg_skinny_linear(const vg_skinny_linear_args* a, vg_stream_t stream);
+
 /* ---- strided Conv1d of the utterance encoder as a GEMM on [B,T,C] rows (modules/conv/layers.py:549-593 ConvNormAct,
  * models/speech/lvtr.py:127-136,203-207): the window gather in front of vg_gemm and its adjoint.
  *   a[b, t, c*K + j] = f(x[b, S*t - pad + j, c])  (0 outside [0,T)),  T_out = (T + 2 pad - K) / S + 1,  f = ReLU if relu

@@ -383,6 +383,58 @@ def test_attention_decode_stream_kernel(B, H, pos, splits):
     assert torch.equal(kc, kv[0]) and torch.equal(vc, kv[1])
 
 
+@pytest.mark.parametrize("B", [1, 5, 64, 100, 200, 256])
+@pytest.mark.parametrize("N,K", [(3072, 1024), (1024, 1024), (4096, 1024), (1024, 4096), (2048, 1024), (520, 1024),
+                                 (200, 1024), (1024, 64), (264, 192)])
+def test_skinny_linear(B, N, K):
+    """vg_skinny_linear (swap-AB tcgen05, cluster split-K through distributed shared memory) against fp32 torch on the
+    same bf16 operands: every plan the host picks for the generation step's shapes (batch tiles 64 / 128 / 256, cluster
+    sizes 1 … 8, ragged feature and batch tails) and every epilogue term"""
+    g = torch.Generator(device="cpu").manual_seed(B * 7919 + N + K)
+    bf = torch.bfloat16
+    x = torch.randn(B, K, generator=g).to(DEV).to(bf)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).to(bf)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(B, N, generator=g).to(DEV).to(bf)
+    mask = (torch.rand(B, generator=g) > 0.3).to(DEV)
+    acc = x.float() @ w.float().t()
+    # plain
+    assert rel_err(ops.skinny_linear(x, w), acc) < tol(bf)
+    # bias + GELU (FFN1), bf16 out
+    y = ops.skinny_linear(x, w, bias, ops.ACT_GELU)
+    assert rel_err(y, torch.nn.functional.gelu(acc + bias)) < tol(bf)
+    # bias + residual + row mask after the residual (FFN2 / out-proj of the layer-by-layer step)
+    y = ops.skinny_linear(x, w, bias, ops.ACT_NONE, res, mask.view(torch.uint8))
+    assert rel_err(y, torch.where(mask[:, None], acc + bias + res.float(), torch.zeros_like(acc))) < tol(bf)
+    # row mask before the residual, ReLU
+    y = ops.skinny_linear(x, w, None, ops.ACT_RELU, res, mask.view(torch.uint8), mask_first=True)
+    assert rel_err(y, torch.where(mask[:, None], torch.relu(acc), torch.zeros_like(acc)) + res.float()) < tol(bf)
+    # f32 output with an f32 residual (the prior / FiLM head)
+    y = ops.skinny_linear(x, w, bias, out_dtype=torch.float32, residual=res.float())
+    assert y.dtype == torch.float32 and rel_err(y, acc + bias + res.float()) < 2e-3
+    # folded RMSNorm in front (1/rms per row from the given sums of squares) and the row statistics of the result
+    if N % 32 == 0:
+        scale = 1.0 + 0.1 * torch.randn(K, generator=g).to(DEV)
+        wn = (w.float() * scale[None, :]).to(bf)
+        x_ss = (x.float() ** 2).sum(-1)
+        y_ss = torch.full((B,), 3.0, device=DEV)
+        zero = torch.ones(B, device=DEV)
+        out = torch.empty(B, N, device=DEV, dtype=bf)
+        ops.skinny_linear(x, wn, bias, ops.ACT_GELU, x_ss=x_ss, norm_eps=1e-6, out=out, y_ss=y_ss, zero_ss=zero)
+        rstd = torch.rsqrt(x_ss / K + 1e-6)
+        want = torch.nn.functional.gelu((x.float() @ wn.float().t()) * rstd[:, None] + bias)
+        assert rel_err(out, want) < tol(bf)
+        assert rel_err(y_ss - 3.0, (out.float() ** 2).sum(-1)) < 1e-3 and float(zero.abs().sum()) == 0.0
+        xin = res.clone()                                           # in place: residual and output are the same buffer
+        ops.skinny_linear(x, w, None, ops.ACT_NONE, xin, out=xin)
+        assert rel_err(xin, acc + res.float()) < tol(bf)
+    # and the autograd-free dispatch of ops.linear takes this route
+    if B <= ops.SKINNY_MAX_ROWS:
+        with torch.no_grad():
+            y2 = ops.linear(x, w, bias, act=ops.ACT_GELU)
+        assert torch.equal(y2, ops.skinny_linear(x, w, bias, ops.ACT_GELU))
+
+
 @pytest.mark.parametrize("cfg", ["64542", "128382"])
 def test_attention_decode_stream_kernel_other_ring_shapes(cfg):
     """the two runner-up ring shapes of the sweep (VG_AD_CFG is read once per process: run the test above in a child)"""

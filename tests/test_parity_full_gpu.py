@@ -191,7 +191,7 @@ def _oracle_generation(model, cfg, B, prompt_len, steps, seed=5):
     return prompt, init_state, eps, outs
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16-step", "bf16-linear", "bf16-layerwise"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16-step", "bf16-linear", "bf16-linear-skinny", "bf16-layerwise"])
 def test_full_config_cached_generation_against_oracle(mode):
     B, P, S = 2, 150, 32
     model, cfg = full_model()
@@ -203,6 +203,7 @@ def test_full_config_cached_generation_against_oracle(mode):
         kind = mode.split("-")[1]
         model.use_decode_engine = kind != "layerwise"
         model.decode_engine_kind = kind
+        model.decode_engine_skinny = mode.endswith("skinny")       # the engine's linears on vg_skinny_linear (folded RMSNorm)
     model.transformer[0].cache_len_hint = P + S + 8
     state, kv = prompt, None
     top2_gap = []
@@ -232,6 +233,7 @@ def test_full_config_cached_generation_against_oracle(mode):
         if mode != "bf16-layerwise":
             eng = model.__dict__["_decode_engines"][B][1]
             assert type(eng).__name__ == ("DecodeStepEngine" if mode == "bf16-step" else "DecodeEngine")
+            assert getattr(eng, "skinny", False) == mode.endswith("skinny")
     assert kv[0].cache.length == P + 1 + S
 
 

@@ -1,3 +1,1 @@
-mkdir -p gpurun_out
-timeout 300 python tools/gemm_epi_bench.py --cold 2>&1 | grep -v Warn | tee gpurun_out/gemm_epi_cold.log
-timeout 300 python tools/gemm_epi_bench.py 2>&1 | grep -v Warn | tee gpurun_out/gemm_epi_hot.log
+timeout 900 python -m pytest tests/test_kernels_gpu.py -q -x -k "skinny and 3072-1024-200" 2>&1 | grep -B30 "^FAILED\|Error" | head -60

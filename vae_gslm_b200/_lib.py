@@ -46,6 +46,20 @@ class GemmArgs(C.Structure):
     ]
 
 
+class SkinnyLinearArgs(C.Structure):
+    _fields_ = [
+        ("x", _p), ("ldx", _i64),
+        ("w", _p), ("ldw", _i64),
+        ("y", _p), ("ldy", _i64),
+        ("bias", _p),
+        ("residual", _p), ("ld_res", _i64),
+        ("row_mask", _p),
+        ("B", _i64), ("N", _i64), ("K", _i64),
+        ("y_dtype", _i32), ("act", _i32), ("mask_before_residual", _i32), ("ss_inv_k", _f32), ("ss_eps", _f32),
+        ("row_ss_in", _p), ("row_ss_out", _p), ("zero_ss", _p),
+    ]
+
+
 class DecodeLinearArgs(C.Structure):
     _fields_ = [
         ("B", _i64), ("N", _i64), ("K", _i64),
@@ -120,6 +134,7 @@ _SIGNATURES = {
     "vg_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_int, _p, _sz, _p]),
     "vg_set_gemm_sm_budget": (C.c_int, [C.c_int]),
     "vg_set_pdl_mode": (C.c_int, [C.c_int]),
+    "vg_skinny_linear": (C.c_int, [_p, _p]),
     "vg_im2col_fwd": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _p]),
     "vg_im2col_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, C.c_int, _p]),
     "vg_colsum_workspace": (_sz, [_i64, _i64]),

@@ -26,9 +26,16 @@ from . import ops
 from ._lib import ACT_GELU, ACT_NONE, ACT_RELU
 
 
+# From this many sequences on the four linear layers of a transformer layer run on vg_skinny_linear (swap-AB tcgen05,
+# cluster split-K through distributed shared memory) instead of vg_decode_linear (mma.sync): measured cross-over,
+# profiles/r02_decode.md.
+SKINNY_FROM_BATCH = 40
+
+
 class DecodeEngine:
-    def __init__(self, model, batch: int, device, overlap: bool = True) -> None:
+    def __init__(self, model, batch: int, device, overlap: bool = True, skinny: Optional[bool] = None) -> None:
         self.model, self.batch, self.device, self.overlap = model, batch, device, overlap
+        self.skinny = (batch >= SKINNY_FROM_BATCH) if skinny is None else bool(skinny)
         stack = model.transformer[0]
         bf = torch.bfloat16
         assert stack.compute_dtype == bf, "the decode engine is the bf16 generation path"
@@ -47,6 +54,12 @@ class DecodeEngine:
                 w1=ops.lowp(lyr.linear1.weight, bf), b1=f32(lyr.linear1.bias) if lyr.linear1.bias is not None else None,
                 w2=ops.lowp(lyr.linear2.weight, bf), b2=f32(lyr.linear2.bias) if lyr.linear2.bias is not None else None,
                 act=lyr._act_id))
+            if self.skinny:
+                # RMSNorm folded into the projection behind it: the norm's scale vector rides in the weight, 1/rms is applied
+                # per row in the epilogue (norm.py:28-32 · attention.py:52 / transformer/layers.py:82)
+                cur = self.layers[-1]
+                cur["w_in_n"] = (lyr.self_attn.in_proj.weight.detach().float() * cur["n1"][None, :]).to(bf).contiguous()
+                cur["w1_n"] = (lyr.linear1.weight.detach().float() * cur["n3"][None, :]).to(bf).contiguous()
         assert stack.linear is not None and stack.linear.bias is None and stack.final_norm is not None
         self.w_stack_in = ops.lowp(stack.linear.weight, bf)
         self.fn_scale, self.fn_eps = f32(stack.final_norm.scale), stack.final_norm.eps
@@ -84,6 +97,15 @@ class DecodeEngine:
         self.ss_a.zero_()
         ops.decode_linear(u16, self.w_stack_in, ws, out=self.x, y_ss=self.ss_a, overlap=False)
         for i, lw in enumerate(self.layers):
+            if self.skinny:
+                ops.skinny_linear(self.x, lw["w_in_n"], x_ss=self.ss_a, norm_eps=lw["eps1"], out=self.qkv, zero_ss=self.ss_b)
+                o = ops.attention_decode(self.qkv, cache.k(kv[i].index), cache.v(kv[i].index), pos, self.slopes,
+                                         cache.pos_dev, out=self.o, tickets=self.tickets)
+                ops.skinny_linear(o, lw["w_out"], residual=self.x, out=self.x, y_ss=self.ss_b)
+                ops.skinny_linear(self.x, lw["w1_n"], lw["b1"], lw["act"], x_ss=self.ss_b, norm_eps=lw["eps3"], out=self.h,
+                                  zero_ss=self.ss_a)
+                ops.skinny_linear(self.h, lw["w2"], lw["b2"], residual=self.x, out=self.x, y_ss=self.ss_a)
+                continue
             ops.decode_linear(self.x, lw["w_in"], ws, norm_scale=lw["n1"], x_ss=self.ss_a, norm_eps=lw["eps1"],
                               out=self.qkv, zero_ss=self.ss_b, overlap=ov)
             o = ops.attention_decode(self.qkv, cache.k(kv[i].index), cache.v(kv[i].index), pos, self.slopes,

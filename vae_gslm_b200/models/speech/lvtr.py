@@ -366,7 +366,7 @@ class LVTR(nn.Module):
                 ent = (stamp, DecodeStepEngine(self, u.shape[0], u.device))
             else:
                 from ...decode import DecodeEngine
-                ent = (stamp, DecodeEngine(self, u.shape[0], u.device))
+                ent = (stamp, DecodeEngine(self, u.shape[0], u.device, skinny=self.__dict__.get("decode_engine_skinny")))
             engines[u.shape[0]] = ent
         return ent[1]
 

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -287,6 +288,59 @@ def rmsnorm_residual(x: torch.Tensor, scale: torch.Tensor, eps: float, mask: Opt
     return _RMSNorm.apply(x, scale, eps, _u8(mask), out_dtype, True)
 
 
+# ------------------------------------------------------------- skinny linear (cached generation step, <= 256 rows)
+SKINNY_LINEAR = os.environ.get("VG_SKINNY_LINEAR", "1") != "0"
+SKINNY_MAX_ROWS = int(os.environ.get("VG_SKINNY_MAX_ROWS", "64"))      # above: gemm_tc's skinny-M plan (profiles/r02_decode.md)
+
+
+def _skinny_ok(x2: torch.Tensor, w: torch.Tensor) -> bool:
+    """bf16 linear layers on few rows (one new frame per sequence) whose inputs need no gradient go to vg_skinny_linear
+    (autograd.Function.forward runs with grad mode off even in training: the callers test ctx.needs_input_grad)"""
+    return (SKINNY_LINEAR and x2.is_cuda and x2.dtype == torch.bfloat16
+            and w.dtype == torch.bfloat16 and x2.shape[0] <= SKINNY_MAX_ROWS and x2.shape[1] % 64 == 0 and w.shape[0] >= 8
+            and x2.stride(0) % 8 == 0 and x2.stride(1) == 1 and w.is_contiguous())
+
+
+@torch.no_grad()
+def skinny_linear(x2: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                  residual: Optional[torch.Tensor] = None, row_mask: Optional[torch.Tensor] = None,
+                  mask_first: bool = False, out_dtype: Optional[torch.dtype] = None, *,
+                  out: Optional[torch.Tensor] = None, x_ss: Optional[torch.Tensor] = None, norm_eps: float = 0.0,
+                  y_ss: Optional[torch.Tensor] = None, zero_ss: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = epilogue(x2 · wᵀ): x2 [B <= 256, K] bf16, w [N, K] bf16 (csrc/skinny_linear.cu: swap-AB tcgen05, cluster
+    split-K through distributed shared memory).  With ``x_ss`` the RMSNorm in front is folded in (w pre-multiplied by the
+    norm's scale, 1/rms applied per row); ``y_ss`` accumulates the row sums of squares of the result, ``zero_ss`` is cleared."""
+    B, K = x2.shape
+    N = w.shape[0]
+    odt = out_dtype or (out.dtype if out is not None else x2.dtype)
+    y = torch.empty((B, N), dtype=odt, device=x2.device) if out is None else out
+    assert y.shape == (B, N) and y.dtype == odt and y.stride(1) == 1
+    a = L.SkinnyLinearArgs()
+    if x_ss is not None:        # RMSNorm folded in: ``w`` already carries the norm's scale vector, x_ss = sum_k x[b,k]^2
+        assert x_ss.dtype == torch.float32 and x_ss.numel() >= B
+        a.row_ss_in, a.ss_inv_k, a.ss_eps = L.ptr(x_ss), 1.0 / K, float(norm_eps)
+    if y_ss is not None:
+        assert y_ss.dtype == torch.float32 and y_ss.numel() >= B
+        a.row_ss_out = L.ptr(y_ss)
+    if zero_ss is not None:
+        assert zero_ss.dtype == torch.float32 and zero_ss.numel() >= B
+        a.zero_ss = L.ptr(zero_ss)
+    a.x, a.ldx, a.w, a.ldw, a.y, a.ldy = L.ptr(x2), x2.stride(0), L.ptr(w), w.stride(0), L.ptr(y), y.stride(0)
+    a.B, a.N, a.K = B, N, K
+    a.y_dtype, a.act, a.mask_before_residual = L.dtype_id(odt), act, int(mask_first)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+        a.bias = L.ptr(bias)
+    if residual is not None:
+        assert residual.dtype == odt and residual.shape == (B, N) and residual.stride(1) == 1
+        a.residual, a.ld_res = L.ptr(residual), residual.stride(0)
+    if row_mask is not None:
+        assert row_mask.numel() == B
+        a.row_mask = L.ptr(row_mask)
+    L.call("vg_skinny_linear", C.byref(a), L.stream())
+    return y
+
+
 # ----------------------------------------------------------------------------------------- Linear
 def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor) -> Optional[torch.Tensor]:
     """dW = dyᵀ·x in fp32.  Parameters that live in a ParamArena (arena.py) get the GEMM written straight into
@@ -315,6 +369,9 @@ class _Linear(torch.autograd.Function):
         odt = out_dtype or x2.dtype
         res2 = _rows2d(residual) if residual is not None else None
         b = bias.detach().float() if bias is not None else None
+        if not any(ctx.needs_input_grad) and _skinny_ok(x2, w) and (res2 is None or res2.dtype == odt):
+            y = skinny_linear(x2, w, b, act, res2, mask_u8, mask_first, odt)
+            return y.view(*x.shape[:-1], N)
         # ReLU's derivative can be read off the output; otherwise the epilogue stores act'(pre) next to act(pre)
         need_pre = act != ACT_NONE and (act != ACT_RELU or residual is not None or mask_u8 is not None)
         pre = torch.empty((x2.shape[0], N), dtype=odt, device=x.device) if need_pre else None
@@ -367,6 +424,11 @@ class _FFN(torch.autograd.Function):
         x2 = _rows2d(x)
         w1c, w2c = lowp(w1, x2.dtype), lowp(w2, x2.dtype)
         M, F = x2.shape[0], w1c.shape[0]
+        if not any(ctx.needs_input_grad) and _skinny_ok(x2, w1c) and _skinny_ok(x2, w2c):
+            h = skinny_linear(x2, w1c, b1.detach().float() if b1 is not None else None, act)
+            y = skinny_linear(h, w2c, b2.detach().float() if b2 is not None else None, ACT_NONE,
+                              _rows2d(residual) if residual is not None else None, mask_u8)
+            return y.view(x.shape[:-1] + (w2c.shape[0],))
         pre = torch.empty((M, F), dtype=x2.dtype, device=x.device)
         h = gemm(x2, w1c, trans_b=True, bias=b1.detach().float() if b1 is not None else None, act=act, preact=pre,
                  preact_is_grad=True)          # `pre` holds act'(W1·x + b1): backward is a plain multiply
