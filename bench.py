@@ -206,7 +206,9 @@ def run_ours(args):
     # lets the host run ahead, so that the device executes the pass back to back and the events bracket kernels only.
     if not mark:                                        # (under ncu every launch is serialised anyway)
         torch.cuda._sleep(int(0.03 * 1.9e9))
+        ops.PROFILE_SPIN = int(60e-6 * 1.9e9)           # and 60 us in front of every timed GEMM keeps the device behind
     train_step._run_eager(device_hyper=False, serial=True)
+    ops.PROFILE_SPIN = 0
     if mark:
         torch.cuda._sleep(1000)
         torch.cuda.synchronize()

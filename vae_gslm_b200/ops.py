@@ -124,6 +124,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
     prof = PROFILE if (PROFILE is not None and a.dtype == torch.bfloat16) else None
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if PROFILE_SPIN:
+            # keep the device BEHIND the host: a short spin kernel in front of the start event gives the host time to
+            # enqueue the GEMM, so that the event pair brackets the kernel and not the idle gap before its launch arrives
+            torch.cuda._sleep(PROFILE_SPIN)
         e0.record()
     L.call("vg_gemm", C.byref(g), be, None, 0, L.stream())
     if prof is not None:
@@ -289,6 +293,7 @@ def rmsnorm_residual(x: torch.Tensor, scale: torch.Tensor, eps: float, mask: Opt
 
 
 # ------------------------------------------------------------- skinny linear (cached generation step, <= 256 rows)
+PROFILE_SPIN = 0            # device clock cycles of spin in front of every profiled GEMM (bench.py's instrumented pass)
 SKINNY_LINEAR = os.environ.get("VG_SKINNY_LINEAR", "1") != "0"
 SKINNY_MAX_ROWS = int(os.environ.get("VG_SKINNY_MAX_ROWS", "64"))      # above: gemm_tc's skinny-M plan (profiles/r02_decode.md)
 
