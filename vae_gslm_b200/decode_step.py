@@ -80,17 +80,18 @@ def pack_units(W: torch.Tensor, R: int, S: int) -> torch.Tensor:
     return v.contiguous().view(n_slabs, S, nkb * R * 64)
 
 
-def attention_splits(n_bh: int, n_warps: int) -> int:
-    """kv-splits per (sequence, head) for the attention phases: items = n_bh * splits are dealt round-robin to the
-    ``n_warps`` worker warps of the grid (one warp per item).  Few (b, h): about half a wave of short items (the merge of
-    the partials by the last arriver grows with the split count); many: the smallest split whose last wave is >= 85 % full."""
-    if n_bh * 4 <= n_warps:
-        return max(1, min(64, n_warps // (2 * n_bh)))
-    for s in (1, 2, 4, 8, 16):
-        items = n_bh * s
-        if items / (-(-items // n_warps) * n_warps) >= 0.85:
-            return s
-    return 16
+def attention_splits(n_bh: int, n_warps: int, keys: int = 400) -> int:
+    """kv-splits per (sequence, head) for the attention phases in warp-per-item mode: items = n_bh * splits are dealt
+    round-robin to the ``n_warps`` worker warps of the grid.  Cost model fitted to the sweep of profiles/r02_decode.md
+    (16 / 24 / 32 sequences x 1 / 2 / 4 / 8 splits, in units of one key per warp): every wave of items costs its keys plus
+    ~40 of start-up (query, row statistics, first HBM round trip), and the merge by the last arriver grows with the split
+    count:  t(s) = ceil(n_bh s / n_warps) (keys / s + 40) + 8 s."""
+    best, best_t = 1, None
+    for s in (1, 2, 3, 4, 6, 8, 12, 16):
+        t = -(-n_bh * s // n_warps) * (keys / s + 40.0) + 8.0 * s
+        if best_t is None or t < best_t:
+            best, best_t = s, t
+    return best
 
 
 class _Args(C.Structure):
@@ -299,7 +300,11 @@ class DecodeStepEngine:
         # ---- attention / barrier state
         # attention: few (sequence, head) pairs → one CTA per (pair, split), up to 4 kv-splits; many → one warp per (pair, split)
         self.attn_coop = 1 if B * H <= G else 0
+        if os.environ.get("VG_DS_COOP"):                      # experiment switch
+            self.attn_coop = int(os.environ["VG_DS_COOP"])
         self.nsplit = max(1, min(4, G // (B * H))) if self.attn_coop else attention_splits(B * H, G * 7)
+        if os.environ.get("VG_DS_NSPLIT"):                    # experiment switch (tools/decode_bench.py sweeps)
+            self.nsplit = int(os.environ["VG_DS_NSPLIT"])
         self.attn_partial = torch.zeros(B * H * self.nsplit * 72, dtype=torch.float32, device=device)
         self.tickets = torch.zeros(B * H, dtype=torch.int32, device=device)
         self.bar_flags = torch.zeros(G + 128, dtype=torch.int32, device=device)

@@ -351,7 +351,7 @@ class LVTR(nn.Module):
         nb = u.shape[0]
         kind = self.decode_engine_kind
         if kind == "auto":
-            kind = "step" if nb <= 12 else ("linear" if nb <= 64 else "none")      # measured cross-overs: profiles/r02_decode.md
+            kind = "step" if nb <= 20 else ("linear" if nb <= 64 else "none")      # measured cross-overs: profiles/r02_decode.md
         step_kind = kind == "step"
         if kind == "none" or nb > (256 if step_kind else self.decode_engine_max_batch):
             return None
