@@ -236,8 +236,8 @@ def run_ours(args):
                 # the GEMMs are timed one at a time (eager, serial pass): against the BURST peak the same number reads
                 "peak_burst": peaks["bf16_burst"], "frac_vs_burst": round(achieved / peaks["bf16_burst"], 4),
                 # DRAM read+write bytes of ONE representative launch (FFN1 forward, bias+GELU+saved derivative, 8000x4096x1024)
-                # from `ncu --set full`: profiles/r01_gemm_gelu_pair_ncu.md (algorithmic bytes of that launch: 155.8e6)
-                "traffic": 112.9e6, "traffic_launch": "ffn1 fwd 8000x4096x1024 (ncu --set full, profiles/r01_gemm_gelu_pair_ncu.md)",
+                # from `ncu --set full`: profiles/r02_gemm_ffn1_ncu.md (algorithmic bytes of that launch: 155.8e6)
+                "traffic": 112.9e6, "traffic_launch": "ffn1 fwd 8000x4096x1024 (ncu --set full of the final build: profiles/r02_gemm_ffn1_ncu.md)",
                 "launches_per_step": len(prof), "gemm_ms_per_step": round(gemm_ms, 3),
                 "share_of_step": round(gemm_ms / step_ms, 3)}
 
