@@ -392,7 +392,8 @@ int vg_im2col_bwd(const void* da, const void* x_relu /* nullable */, void* dx, i
  * features x `nkb` 64-wide k-blocks of one linear layer as a swap-AB tcgen05 GEMM whose weight slab comes from the CTA's
  * own packed byte stream (`wstream + wstream_off[cta]`: per unit, per k-block, R/8 SWIZZLE_128B atoms of 8 rows x 64 bf16,
  * in consumption order) and whose X operand the CTA forms from `x` (x_kind 0: bf16 rows; 1: f32 rows * vec[k], optionally
- * accumulating the row sum-of-squares into ss_out; 2: act(f32 rows * rsqrt(ss_in[b]*inv_k + eps) + vec[k])).  The
+ * accumulating the row sum-of-squares into ss_out; 2: act(f32 rows * rsqrt(ss_in[b]*inv_k + eps) + vec[k]); 3: the
+ * attention output merged from the kv-split partials `attn_partial` — see late_merge).  The
  * accumulator rows are reduced (red.global.add.f32) or stored into acc[b*ldacc + n0 + r] (+ bias_out[n0 + r]).
  * phase_kind[p] < 0: GEMM phase; >= 0: attention phase of that layer over the head-major cache
  * [L][2][B][H][Tmax][64] bf16 (reads the QKV sums of the phase before, appends k/v at *pos_dev).
@@ -436,6 +437,8 @@ typedef struct {
   int32_t NP, grid, B, Bp, H, Tmax, nsplit, barrier_mode, advance_pos;
   int32_t rep;                           /* copies of the batch rows in the X tile / accumulator: 4 (B <= 32), 2 (<= 64), 1 */
   int32_t attn_coop;                     /* 1: one CTA per attention item (few sequences); 0: one warp per item */
+  int32_t late_merge;                    /* 1: attention phases publish (m, l, o) per kv-split only; the out-projection unit (x_kind 3,
+                                            x = attn_partial) merges and normalises them while forming its X operand */
 } vg_decode_step_args;
 size_t vg_decode_step_task_bytes(void);
 size_t vg_decode_step_smem_bytes(int32_t n_phases);

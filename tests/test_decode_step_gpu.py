@@ -81,7 +81,16 @@ def phase_buffer(eng, last, B):
     if last.startswith("qkv"):
         return eng.qkv_acc.view(B, -1)
     if last.startswith("attn"):
-        return eng.o
+        if not eng.late_merge:
+            return eng.o
+        # late merge: the phase publishes (m, l, o[64]) per kv-split (exp2 domain); merge them as the out-projection does
+        H = eng.nheads
+        pt = eng.attn_partial.view(B * H, eng.nsplit, 72)
+        m, l, o = pt[..., 0], pt[..., 1], pt[..., 8:]
+        w = torch.exp2(m - m.max(-1, keepdim=True).values)
+        w = torch.where(torch.isfinite(m), w, torch.zeros_like(w))
+        att = (w[..., None] * o).sum(1) / (w * l).sum(1, keepdim=True)
+        return bf(att.view(B, H * 64))
     if last.startswith("ffn1_"):
         return eng.f1_acc.view(B, -1)
     if last == "split":
@@ -193,3 +202,30 @@ def test_decode_step_planner_contract():
                     for k in range(0, 64, 8):
                         addr = (kb * R * 128 + (row // 8) * 1024 + (row % 8) * 128 + (((k // 8) ^ (row % 8)) * 16)) // 2
                         assert torch.equal(u[addr:addr + 8], W[slab * R + row, s * nkb * 64 + kb * 64 + k: s * nkb * 64 + kb * 64 + k + 8])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 16])
+def test_decode_step_kernel_ticket_merge_route(golden, B):
+    """the in-phase merge of the kv-split partials (ticket + last arriver; late_merge=False) stays correct: one CTA per
+    item (B = 1, 4 splits) and one warp per item (B = 16, 4 splits)"""
+    model, vocab = build(False, golden)
+    kv, u16 = prefill(model, vocab, B, 70)
+    cache = kv[0].cache
+    pos = cache.length
+    snapshot = cache.buf.clone()
+    ref = mirror_step(model, u16, snapshot, pos)
+    for k in (3, 0):
+        cache.buf.copy_(snapshot)
+        cache.length = pos
+        eng = DecodeStepEngine(model, B, DEV, debug_phases=k, late_merge=False)
+        assert eng.nsplit > 1 and not eng.late_merge
+        for rep in range(2):
+            cache.buf.copy_(snapshot)
+            cache.length = pos
+            eng.run(u16, kv)
+        torch.cuda.synchronize()
+        last = eng.phase_names[-1]
+        want = ref["logits"] if last == "heads" else ref[last]
+        assert rel(phase_buffer(eng, last, B), want) < (8e-3 if k else 1.5e-2)
+        assert int(eng.tickets.abs().sum()) == 0

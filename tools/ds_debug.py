@@ -136,7 +136,9 @@ for k in [int(x) for x in args.prefix.split(",")]:
         got, want = eng.qkv_acc.view(B, -1), ref[last]
     elif last.startswith("attn"):
         i = int(last[4:])
-        got, want = eng.o, ref[last]
+        got, want = (eng.o if not eng.late_merge else None), ref[last]
+        if got is None:
+            continue
         print(f"   cache append k {rel(cache.buf[i, 0, :, :, pos].reshape(B, -1), ref[f'k{i}']):.2e} "
               f"v {rel(cache.buf[i, 1, :, :, pos].reshape(B, -1), ref[f'v{i}']):.2e}")
     elif last.startswith("ffn1_"):

@@ -1,3 +1,5 @@
-mkdir -p gpurun_out
-bash tools/run_gpu_ncu_gemm.sh
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:skinny_linear -s 20 -c 1 -f -o gpurun_out/prof_skinny_b64 python tools/skinny_bench.py 64 > /dev/null 2>&1; ls -la gpurun_out/prof_skinny_b64.ncu-rep
+for ns in 4 6 9; do echo "== B=1 nsplit $ns"; VG_DS_NSPLIT=$ns timeout 300 python tools/decode_bench.py 1 --kind=step 2>&1 | grep -v Warning | cut -c1-80; done
+for ns in 2 4; do echo "== B=2 nsplit $ns"; VG_DS_NSPLIT=$ns timeout 300 python tools/decode_bench.py 2 --kind=step 2>&1 | grep -v Warning | cut -c1-80; done
+echo "== B=8 warp mode nsplit 8 / 4"; VG_DS_COOP=0 VG_DS_NSPLIT=8 timeout 300 python tools/decode_bench.py 8 --kind=step 2>&1 | grep -v Warning | cut -c1-80
+VG_DS_COOP=0 VG_DS_NSPLIT=4 timeout 300 python tools/decode_bench.py 8 --kind=step 2>&1 | grep -v Warning | cut -c1-80
+echo "== B=8 direct (no late merge)"; VG_DS_LATE_MERGE=0 timeout 300 python tools/decode_bench.py 8 --kind=step 2>&1 | grep -v Warning | cut -c1-80

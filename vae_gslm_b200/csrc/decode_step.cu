@@ -190,6 +190,53 @@ __device__ __forceinline__ void ds_transform(const DsArgs& a, const DsTask& t, D
   const int kind = t.x_kind;
   if (wt < 64) ds_cp_async_wait_all();          // the prefetch of this unit's vectors (issued by these two warps)
   ds_named_bar(2, DS_WORKERS);
+  if (kind == 3) {
+    // x = the attention output, formed from the kv-split partials of the attention phase (late merge): for 8 consecutive
+    // dims of one (sequence, head): o = sum_s 2^(m_s - M) o_s / sum_s 2^(m_s - M) l_s, rounded to bf16
+    const int nsplit = a.nsplit, Hh = a.H;
+    for (int c = 0; c < nchunks; ++c) {
+      const int slot = xcount & 1;
+      const uint32_t use = xcount >> 1;
+      if (use > 0) ds_mbar_wait(&sh.xempty[slot], (use - 1) & 1, a, 10, phase);
+      uint8_t* dst = xs + slot * DS_XSLOT;
+      const int kc0 = c * xkb * 64;
+      for (int item = wt; item < items; item += DS_WORKERS) {
+        const int b = item >> lg;
+        const int rem = item & (per_b - 1);
+        const int j = rem >> 3, g = rem & 7;
+        const int k = t.k0 + kc0 + (rem << 3);               // first of the 8 model dims of this item
+        const int h = k >> 6, d0 = k & 63;
+        const float* pp = reinterpret_cast<const float*>(t.x) + ((size_t)(b * Hh + h) * nsplit) * (DS_HD + 8);
+        float M = -CUDART_INF_F;
+        for (int s2 = 0; s2 < nsplit; ++s2) M = fmaxf(M, __ldcg(pp + s2 * (DS_HD + 8)));
+        float L = 0.f, o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        for (int s2 = 0; s2 < nsplit; ++s2) {
+          const float2 ml = __ldcg(reinterpret_cast<const float2*>(pp + s2 * (DS_HD + 8)));
+          const float4 v0 = __ldcg(reinterpret_cast<const float4*>(pp + s2 * (DS_HD + 8) + 8 + d0));
+          const float4 v1 = __ldcg(reinterpret_cast<const float4*>(pp + s2 * (DS_HD + 8) + 8 + d0) + 1);
+          const float w = (ml.x == -CUDART_INF_F) ? 0.f : ex2_approx(ml.x - M);
+          L = fmaf(ml.y, w, L);
+          o[0] = fmaf(v0.x, w, o[0]); o[1] = fmaf(v0.y, w, o[1]); o[2] = fmaf(v0.z, w, o[2]); o[3] = fmaf(v0.w, w, o[3]);
+          o[4] = fmaf(v1.x, w, o[4]); o[5] = fmaf(v1.y, w, o[5]); o[6] = fmaf(v1.z, w, o[6]); o[7] = fmaf(v1.w, w, o[7]);
+        }
+        const float inv = L > 0.f ? 1.0f / L : 0.f;
+        uint4 packed;
+        packed.x = ds_pack_bf16(o[0] * inv, o[1] * inv); packed.y = ds_pack_bf16(o[2] * inv, o[3] * inv);
+        packed.z = ds_pack_bf16(o[4] * inv, o[5] * inv); packed.w = ds_pack_bf16(o[6] * inv, o[7] * inv);
+        for (int r = 0; r < a.rep; ++r) {
+          const int br = b + r * (128 / a.rep);
+          *reinterpret_cast<uint4*>(dst + j * (Bp * 128) + (br >> 3) * 1024 + (br & 7) * 128 + ((g ^ (br & 7)) << 4)) = packed;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&sh.xfull[slot]);
+      if (c == 0) DS_TRACE(7, 64);
+      ++xcount;
+    }
+    return;
+  }
   for (int c = 0; c < nchunks; ++c) {
     const int slot = xcount & 1;
     const uint32_t use = xcount >> 1;
@@ -418,6 +465,17 @@ __device__ __forceinline__ void ds_attn_finish(const DsArgs& a, const DsAttnStat
   const int HD = a.H * DS_HD, nsplit = a.nsplit;
   const int grp = lane >> 3, sub = lane & 7;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.attn_out);
+  if (a.late_merge) {
+    // the split partials (m, l, o[64]) are all this phase publishes: the out-projection's X transform merges and
+    // normalises them when it forms its operand (x_kind 3) — no ticket, no last-arriver round trips on the critical path
+    float* pp = a.attn_partial + ((size_t)bh * nsplit + split) * (DS_HD + 8);
+    if (grp == 0) {
+      __stcg(reinterpret_cast<float4*>(pp + 8 + sub * 8), make_float4(st.acc[0], st.acc[1], st.acc[2], st.acc[3]));
+      __stcg(reinterpret_cast<float4*>(pp + 8 + sub * 8) + 1, make_float4(st.acc[4], st.acc[5], st.acc[6], st.acc[7]));
+      if (sub == 0) __stcg(reinterpret_cast<float2*>(pp), make_float2(st.m, st.l));
+    }
+    return;
+  }
   if (nsplit == 1) {
     if (grp == 0) {
       const float inv = st.l > 0.f ? 1.0f / st.l : 0.f;

@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -104,12 +104,13 @@ class _Args(C.Structure):
         ("inv_d", C.c_float), ("eps", C.c_float), ("scale", C.c_float),
         ("NP", C.c_int32), ("grid", C.c_int32), ("B", C.c_int32), ("Bp", C.c_int32), ("H", C.c_int32),
         ("Tmax", C.c_int32), ("nsplit", C.c_int32), ("barrier_mode", C.c_int32), ("advance_pos", C.c_int32),
-        ("rep", C.c_int32), ("attn_coop", C.c_int32),
+        ("rep", C.c_int32), ("attn_coop", C.c_int32), ("late_merge", C.c_int32),
     ]
 
 
 class DecodeStepEngine:
-    def __init__(self, model, batch: int, device, barrier_mode: int = -1, grid: int = 0, debug_phases: int = 0) -> None:
+    def __init__(self, model, batch: int, device, barrier_mode: int = -1, grid: int = 0, debug_phases: int = 0,
+                 late_merge: Optional[bool] = None) -> None:
         lib = L.load()
         assert lib.vg_decode_step_task_bytes() == TASK_DTYPE.itemsize, "task struct layout drifted from include/vgslm.h"
         self.model, self.batch, self.device = model, batch, device
@@ -180,6 +181,19 @@ class DecodeStepEngine:
             keep.append(t)
             return t.data_ptr()
 
+        # ---- attention phases: how the (sequence, head, kv-split) items are dealt, and where their partials go
+        # attention: few (sequence, head) pairs → one CTA per (pair, split), up to 4 kv-splits; many → one warp per (pair, split)
+        self.attn_coop = 1 if B * H <= G else 0
+        if os.environ.get("VG_DS_COOP"):                      # experiment switch
+            self.attn_coop = int(os.environ["VG_DS_COOP"])
+        self.nsplit = max(1, min(4, G // (B * H))) if self.attn_coop else attention_splits(B * H, G * 7)
+        if os.environ.get("VG_DS_NSPLIT"):                    # experiment switch (tools/decode_bench.py sweeps)
+            self.nsplit = int(os.environ["VG_DS_NSPLIT"])
+        self.attn_partial = torch.zeros(B * H * self.nsplit * 72, dtype=torch.float32, device=device)
+        self.tickets = torch.zeros(B * H, dtype=torch.int32, device=device)
+        # late merge (default): the attention phases only publish (m, l, o) per kv-split; the out-projection's X transform
+        # merges and normalises them (no ticket / last-arriver round trips on the critical path of the attention phase)
+        self.late_merge = int(os.environ.get("VG_DS_LATE_MERGE", "1") != "0") if late_merge is None else int(late_merge)
         rmax = 256 if B <= 32 else 128          # output features per unit (= the N of the MMA): see split_factor
         # ---- phases
         rs_log: List[Tuple[int, int]] = []
@@ -220,7 +234,8 @@ class DecodeStepEngine:
                 ss_out=ss_ptr(2 * i))))
             phases.append(dict(kind=i, name=f"attn{i}", aux=None, units=[]))
             phases.append(dict(kind=-1, name=f"out{i}", aux=zero_job("qkv", B * 3 * d), units=gemm_units(
-                sa.out_proj.weight, B, self.o.data_ptr(), d, 0, self.h.data_ptr(), d)))
+                sa.out_proj.weight, B, self.attn_partial.data_ptr() if self.late_merge else self.o.data_ptr(), d,
+                3 if self.late_merge else 0, self.h.data_ptr(), d)))
             phases.append(dict(kind=-1, name=f"ffn1_{i}", aux=None, units=gemm_units(
                 lyr.linear1.weight, B, self.h.data_ptr(), d, 1, self.f1_acc.data_ptr(), ffd, vec_ptr=vec(lyr.norm3.scale),
                 ss_out=ss_ptr(2 * i + 1))))
@@ -297,16 +312,7 @@ class DecodeStepEngine:
         self._keep = keep
         self.smem = lib.vg_decode_step_smem_bytes(NP)
         assert self.smem <= 227 * 1024, self.smem
-        # ---- attention / barrier state
-        # attention: few (sequence, head) pairs → one CTA per (pair, split), up to 4 kv-splits; many → one warp per (pair, split)
-        self.attn_coop = 1 if B * H <= G else 0
-        if os.environ.get("VG_DS_COOP"):                      # experiment switch
-            self.attn_coop = int(os.environ["VG_DS_COOP"])
-        self.nsplit = max(1, min(4, G // (B * H))) if self.attn_coop else attention_splits(B * H, G * 7)
-        if os.environ.get("VG_DS_NSPLIT"):                    # experiment switch (tools/decode_bench.py sweeps)
-            self.nsplit = int(os.environ["VG_DS_NSPLIT"])
-        self.attn_partial = torch.zeros(B * H * self.nsplit * 72, dtype=torch.float32, device=device)
-        self.tickets = torch.zeros(B * H, dtype=torch.int32, device=device)
+        # ---- barrier state
         self.bar_flags = torch.zeros(G + 128, dtype=torch.int32, device=device)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self.debug = torch.zeros(8, dtype=torch.int64, device=device)
@@ -334,7 +340,7 @@ class DecodeStepEngine:
         a.inv_d, a.eps, a.scale = 1.0 / self.dim, self.eps, 1.0 / 8.0
         a.NP, a.grid, a.B, a.Bp, a.H = self.NP, self.grid, self.batch, self.Bp, self.nheads
         a.Tmax, a.nsplit, a.barrier_mode, a.advance_pos = cache.max_len, self.nsplit, self.barrier_mode, advance
-        a.rep, a.attn_coop = self.rep, self.attn_coop
+        a.rep, a.attn_coop, a.late_merge = self.rep, self.attn_coop, self.late_merge
         return a
 
     @torch.no_grad()
