@@ -1,5 +1,3 @@
-for ns in 4 6 9; do echo "== B=1 nsplit $ns"; VG_DS_NSPLIT=$ns timeout 300 python tools/decode_bench.py 1 --kind=step 2>&1 | grep -v Warning | cut -c1-80; done
-for ns in 2 4; do echo "== B=2 nsplit $ns"; VG_DS_NSPLIT=$ns timeout 300 python tools/decode_bench.py 2 --kind=step 2>&1 | grep -v Warning | cut -c1-80; done
-echo "== B=8 warp mode nsplit 8 / 4"; VG_DS_COOP=0 VG_DS_NSPLIT=8 timeout 300 python tools/decode_bench.py 8 --kind=step 2>&1 | grep -v Warning | cut -c1-80
-VG_DS_COOP=0 VG_DS_NSPLIT=4 timeout 300 python tools/decode_bench.py 8 --kind=step 2>&1 | grep -v Warning | cut -c1-80
-echo "== B=8 direct (no late merge)"; VG_DS_LATE_MERGE=0 timeout 300 python tools/decode_bench.py 8 --kind=step 2>&1 | grep -v Warning | cut -c1-80
+timeout 900 python -m pytest tests/test_decode_step_gpu.py -q -x 2>&1 | tail -2
+echo "== prefetch on"; timeout 600 python tools/decode_bench.py 1 4 8 16 --kind=step 2>&1 | grep -v Warning | cut -c1-80
+echo "== prefetch off"; VG_DS_ATTN_PREFETCH=0 timeout 600 python tools/decode_bench.py 1 4 8 16 --kind=step 2>&1 | grep -v Warning | cut -c1-80
