@@ -1,3 +1,5 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_kernels_gpu.py -q -x -k "gemm" 2>&1 | tail -5
-for t in 1 0; do echo "== M=5120 VG_GEMM_TAIL=$t"; VG_GEMM_TAIL=$t timeout 300 python tools/gemm_bench.py 5120 --quick 2>&1 | grep "fwd\|dgrad" | awk '{print $1,$2,$3,$5,$6,$7,$8}' | head -8; done 2>&1 | tee gpurun_out/gemm_tail.log
+for p in 0 1; do echo "== VG_TRAIN_PDL=$p"; VG_TRAIN_PDL=$p timeout 900 python bench.py --no-decode --no-gpu-reference --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
+print(d['value'], d['ms_per_step'], r['achieved'], d['loss'], {k:(v['value'],v['ms_per_step']) for k,v in d['shapes'].items()})"; done
+VG_TRAIN_PDL=1 timeout 600 python -m pytest tests/test_model_gpu.py -q -x -k "train_step or gradient_accumulation or first_writer" 2>&1 | tail -2

@@ -80,6 +80,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                    float* __restrict__ lse, const int32_t* __restrict__ kv_len, const float* __restrict__ slopes,
                    AttnTcShape sh) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL-launched kernel behind may start its prologue (vg_set_pdl_mode)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -699,6 +700,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 __global__ void attn_tc_delta_kernel(const __nv_bfloat16* __restrict__ dout, int64_t ld_dout,
                                      const __nv_bfloat16* __restrict__ out, int64_t ld_out, float* __restrict__ delta,
                                      int B, int H, int Tq) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL-launched kernel behind may start its prologue (vg_set_pdl_mode)
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 8;      // 8 lanes per (b,h,i) row
   const int sub = threadIdx.x & 7;
   if (w >= (int64_t)B * H * Tq) return;     // whole 8-lane groups exit together; shuffles below stay in-group
@@ -720,6 +722,7 @@ __global__ void attn_tc_delta_kernel(const __nv_bfloat16* __restrict__ dout, int
 
 __global__ void attn_tc_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t ld_dq,
                                           int64_t rows, int C) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL-launched kernel behind may start its prologue (vg_set_pdl_mode)
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // over rows * C/8
   const int c8 = C / 8;
   if (i >= rows * c8) return;

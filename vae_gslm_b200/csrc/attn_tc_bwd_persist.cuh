@@ -15,6 +15,7 @@ attn_tc_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
                    const __grid_constant__ CUtensorMap tmDV, const float* __restrict__ lse,
                    const float* __restrict__ delta,
                    const int32_t* __restrict__ kv_len, const float* __restrict__ slopes, AttnTcShape sh) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL-launched kernel behind may start its prologue (vg_set_pdl_mode)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);

@@ -9,6 +9,7 @@ namespace vg {
 template <typename T>
 __global__ void __launch_bounds__(256)
 mask_rows_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mask, T* __restrict__ y, int64_t rows, int cols8) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL-launched kernel behind may start its prologue (vg_set_pdl_mode)
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // over rows * cols/8
   if (i >= rows * cols8) return;
   const int64_t r = i / cols8;
@@ -33,6 +34,7 @@ mask_rows_scalar_kernel(const T* __restrict__ x, const uint8_t* __restrict__ mas
 template <typename T>
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ src, T* __restrict__ dx, int64_t n8, int act) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL-launched kernel behind may start its prologue (vg_set_pdl_mode)
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   Vec8<T> g, s;

@@ -62,6 +62,7 @@ rmsnorm_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const fl
                    const float* __restrict__ rstd, const uint8_t* __restrict__ mask,
                    const TX* __restrict__ dres, TX* __restrict__ dx, float* __restrict__ partial,
                    int64_t rows, int dim) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a PDL-launched kernel behind may start its prologue (vg_set_pdl_mode)
   __shared__ float red[kRmsWarps][32 * 8];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;

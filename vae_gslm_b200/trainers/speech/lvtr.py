@@ -4,6 +4,8 @@ single-process training step around it (``TrainStep``).  The Lightning shell of 
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Mapping, Optional
 
 import torch
@@ -100,6 +102,7 @@ class TrainStep:
                  kld_weight: float = 0.04, betas=(0.9, 0.98), eps: float = 1e-8, use_cuda_graph: bool = True,
                  warmup_iters: int = 3, overlap_grads: bool = True, accumulate: int = 1,
                  preserve_state: bool = True) -> None:
+        self.pdl = int(os.environ.get("VG_TRAIN_PDL", "1"))
         self.model, self.arena, self.reducer = model, arena, reducer
         self.lr, self.betas, self.eps = lr, betas, eps
         self.accumulate = int(accumulate)
@@ -170,6 +173,14 @@ class TrainStep:
 
     # the work of one step, on whatever stream is current
     def _body(self, device_hyper: bool) -> None:
+        from ... import ops
+        # VG_TRAIN_PDL (default 1; 0 = plain stream order): the tcgen05 GEMMs and RMSNorm forwards of the step are launched with the programmatic-dependent-
+        # launch attribute (their barrier / TMEM set-up overlaps the tail of the kernel in front; no weight prefetch:
+        # bit 0 only — in training the B operand of a GEMM is not always a static weight)
+        with ops.pdl_mode(self.pdl):
+            self._body_impl(device_hyper)
+
+    def _body_impl(self, device_hyper: bool) -> None:
         from ... import ops
         if self.grad_stream is None and self.loss.is_cuda and self.overlap_grads:
             # one parameter-gradient stream per process and device: the reducer keeps every side stream it has seen in
