@@ -519,7 +519,7 @@ def cpu_baseline_sample(lr, B=2, T=1000):
             "host_cpus": os.cpu_count()}
 
 
-def gpu_reference_block(dev, lr, B, T, steps=5, warmup=2):
+def gpu_reference_block(dev, lr, B, T, steps=4, warmup=3):
     """the stock-PyTorch bar: the reference's own modules — dense-mask SDPA, cuBLAS, cuDNN,
     ~40 small kernels per layer — under torch.autocast(bf16) with TF32 matmuls (scripts/train.py:44) and fused AdamW, on
     the SAME B200 and the same synthetic batch, timed with CUDA events.  Its RNG draws are its own (the timing does not
@@ -533,15 +533,19 @@ def gpu_reference_block(dev, lr, B, T, steps=5, warmup=2):
         for _ in range(warmup):
             step(batch, rng)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            loss = step(batch, rng)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        # eager PyTorch is partly host-bound (~40 short kernels per layer): take the BEST of three timed blocks, so that a
+        # busy host core does not flatter the comparison
+        ms = float("inf")
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = step(batch, rng)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = min(ms, e0.elapsed_time(e1) / steps)
         out = {"frames_per_sec": round(B * T / (ms / 1e3), 1), "ms_per_step": round(ms, 2), "kind": step.kind,
-               "precision": "torch.autocast(bf16) + TF32 matmul, fused AdamW", "batch": B, "frames": T, "steps": steps,
+               "precision": "torch.autocast(bf16) + TF32 matmul, fused AdamW", "batch": B, "frames": T, "steps": steps, "timing": "best of 3 blocks",
                "loss": float(loss), "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
     except Exception as e:                                   # noqa: BLE001
         out = {"unavailable": repr(e)[:300]}
