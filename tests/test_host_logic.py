@@ -189,3 +189,33 @@ def test_seeded_init_is_bit_identical_to_reference():
                 or hashlib.sha256(t.numpy().tobytes()).hexdigest() != e["sha256"]:
             bad.append(e["name"])
     assert not bad, bad[:10]
+
+
+def test_decode_planners():
+    """host-side planning of the cached generation step (no GPU): kv-split choices of the two decode attention paths, the
+    unit decomposition of the persistent step kernel, and the packed weight image it streams"""
+    from vae_gslm_b200.decode_step import attention_splits, pack_units, split_factor
+    from vae_gslm_b200.ops import decode_splits
+    # vg_attn_decode: splits cost more than the imbalance they remove at every cache length of the recipe
+    assert all(decode_splits(b * 16, 683) == 1 for b in (1, 8, 64, 256))
+    assert decode_splits(16, 4096) > 1 and decode_splits(4096, 4096) == 1
+    # the step kernel's warp-per-item attention: the fitted cost model reproduces the measured optima
+    n_warps = 148 * 7
+    assert attention_splits(16 * 16, n_warps) == 4 and attention_splits(24 * 16, n_warps) == 2
+    assert attention_splits(32 * 16, n_warps) == 2 and attention_splits(256 * 16, n_warps) == 1
+    # units: R output features x K / S inputs, about 128 per phase, k-blocks per unit a power of two
+    for (N, K) in ((3072, 1024), (1024, 1024), (4096, 1024), (1024, 4096), (2048, 1024), (1024, 64)):
+        for rmax in (128, 256):
+            R, S = split_factor(N, K, rmax=rmax)
+            nkb = K // 64 // S
+            assert R % 16 == 0 and R <= rmax and nkb >= 1 and nkb & (nkb - 1) == 0
+            assert -(-N // R) * S <= 148
+    # the packed image is the SWIZZLE_128B K-major layout of each [R x 64] slab: row r of a slab keeps its 16-byte group g
+    # at position g ^ (r & 7)
+    W = torch.arange(32 * 128, dtype=torch.float32).view(32, 128).to(torch.bfloat16)
+    p = pack_units(W, 16, 2)                                  # 2 slabs x 2 k-slices x (1 k-block * 16 rows * 64)
+    assert p.shape == (2, 2, 16 * 64)
+    slab = p[1, 1].view(16, 8, 8)                             # rows 16..31, k 64..127
+    for r in (0, 3, 9):
+        for g in (0, 5):
+            assert torch.equal(slab[r, g ^ (r & 7)], W[16 + r, 64 + g * 8: 64 + g * 8 + 8])
