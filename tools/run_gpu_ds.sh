@@ -1,9 +1,2 @@
-mkdir -p gpurun_out
-VG_BENCH_GEMM_TABLE=1 timeout 1500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
-python -c "
-import json
-d=json.loads(open('gpurun_out/bench_n1.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'], d['mfu_vs_measured_sustained'])
-print(d['gpu_reference']); print(d['cpu_baseline'])
-print({k:(v['value'],v['ms_per_step']) for k,v in d['shapes'].items()})
-for k,v in d['decode'].items(): print(k, v.get('ms_per_step'), v.get('frac'), v.get('path'))"
+for p in 0 1 0 1; do VG_DECODE_PDL=$p timeout 300 python tools/ddim_bench.py 2>&1 | grep VG_DECODE_PDL; done
+timeout 600 python -m pytest tests/test_model_gpu.py -q -x -k "ddim" 2>&1 | tail -2
