@@ -191,9 +191,11 @@ def _oracle_generation(model, cfg, B, prompt_len, steps, seed=5):
     return prompt, init_state, eps, outs
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16-step", "bf16-linear", "bf16-linear-skinny", "bf16-layerwise"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16-step", "bf16-linear", "bf16-linear-skinny", "bf16-layerwise",
+                                  "bf16-layerwise-b80"])
 def test_full_config_cached_generation_against_oracle(mode):
-    B, P, S = 2, 150, 32
+    # b80: 80 sequences — the layer-by-layer step whose FFN takes the split-K route of ops.ffn (65..256 rows)
+    B, P, S = (80, 150, 6) if mode.endswith("b80") else (2, 150, 32)
     model, cfg = full_model()
     model.eval()
     prompt, init_state, eps, ref = _oracle_generation(model, cfg, B, P, S)
@@ -230,7 +232,7 @@ def test_full_config_cached_generation_against_oracle(mode):
     if not fp32:
         scale = float(ref[0]["logits"].abs().max())
         assert all(gp < 3e-2 * scale for gp in top2_gap), top2_gap
-        if mode != "bf16-layerwise":
+        if kind != "layerwise":
             eng = model.__dict__["_decode_engines"][B][1]
             assert type(eng).__name__ == ("DecodeStepEngine" if mode == "bf16-step" else "DecodeEngine")
             assert getattr(eng, "skinny", False) == mode.endswith("skinny")
