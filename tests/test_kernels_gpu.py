@@ -429,7 +429,8 @@ def test_skinny_linear(B, N, K):
         ops.skinny_linear(x, w, None, ops.ACT_NONE, xin, out=xin)
         assert rel_err(xin, acc + res.float()) < tol(bf)
     # and the autograd-free dispatch of ops.linear takes this route
-    if B <= ops.SKINNY_MAX_ROWS:
+    # (every layer up to SKINNY_MAX_ROWS rows; up to SKINNY_MIXED_ROWS rows the layers with <= 1024 output features)
+    if B <= ops.SKINNY_MAX_ROWS or (B <= ops.SKINNY_MIXED_ROWS and N <= 1024):
         with torch.no_grad():
             y2 = ops.linear(x, w, bias, act=ops.ACT_GELU)
         assert torch.equal(y2, ops.skinny_linear(x, w, bias, ops.ACT_GELU))

@@ -285,9 +285,68 @@ skinny_linear_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
 
 using namespace vg;
 
+typedef void (*SkKernel)(const CUtensorMap, const CUtensorMap, const SkParams);
+
+static SkKernel sk_kernel(int bt) {
+  return bt == 64 ? skinny_linear_kernel<64> : (bt == 128 ? skinny_linear_kernel<128> : skinny_linear_kernel<256>);
+}
+
+// ring depth and dynamic shared memory of one CTA for batch tile `bt` and `nkb` k-blocks per CTA
+static void sk_smem(int bt, int nkb, int* ns_out, size_t* smem_out) {
+  const int stage = SK_W_BYTES + bt * 128;
+  int ns = (200 * 1024) / stage;
+  if (ns > SK_MAX_STAGES) ns = SK_MAX_STAGES;
+  if (ns > nkb) ns = nkb;
+  const int ring = ns * stage > bt * SK_FT * 4 ? ns * stage : bt * SK_FT * 4;
+  *ns_out = ns;
+  *smem_out = 1024 + (size_t)ring + sizeof(SkBars) + 64;
+}
+
+static int sk_set_smem_attr(int bt) {
+  static bool attr_set[3] = {false, false, false};
+  const int ki = bt == 64 ? 0 : (bt == 128 ? 1 : 2);
+  if (!attr_set[ki]) {
+    VG_CUDA(cudaFuncSetAttribute(sk_kernel(bt), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[ki] = true;
+  }
+  return 0;
+}
+
+// How many clusters of `s` CTAs of this shape the device holds at once (a cluster needs its s SMs inside one GPC, so this
+// is less than SMs / s: e.g. 16 clusters of 8 would need every GPC to give exactly two).  Cached per (bt, s, ring depth).
+static int sk_resident_clusters(int bt, int s, int nkb, int sms) {
+  static int cache[3][4][SK_MAX_STAGES + 1] = {};
+  const int ki = bt == 64 ? 0 : (bt == 128 ? 1 : 2);
+  const int si = s == 1 ? 0 : (s == 2 ? 1 : (s == 4 ? 2 : 3));
+  int ns; size_t smem;
+  sk_smem(bt, nkb, &ns, &smem);
+  int& slot = cache[ki][si][ns];
+  if (slot) return slot;
+  int n = 0;
+  if (sk_set_smem_attr(bt) == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(s * sms));
+    cfg.blockDim = dim3(SK_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)s;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)sk_kernel(bt), &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+  }
+  if (n <= 0) n = s == 8 ? 14 : sms / s;                      // the query failed: a conservative guess
+  slot = n;
+  return n;
+}
+
 // (BT, S) for one shape: one wave of clusters over the SMs with the fewest bytes through each SM's shared memory;
-// a split costs the distributed-shared-memory exchange of the partial tile.
-static void sk_plan(int64_t B, int64_t N, int64_t K, int sms, int* bt_out, int* s_out) {
+// a split costs the distributed-shared-memory exchange of the partial tile.  Above 64 rows the wave count comes from
+// the number of clusters the device really holds at once (sk_resident_clusters); the plans up to 64 rows were swept
+// shape by shape on the device (profiles/r02_decode.md 3b) and keep the SM-count rule they were fitted with.
+static void sk_plan(int64_t B, int64_t N, int64_t K, int sms, bool residency, int* bt_out, int* s_out) {
   const int64_t kb = K / 64;
   const int64_t ft = ceil_div(N, SK_FT);
   double best = 1e30;
@@ -298,7 +357,11 @@ static void sk_plan(int64_t B, int64_t N, int64_t K, int sms, int* bt_out, int* 
     for (int s = 1; s <= 8; s *= 2) {
       if (kb % s || bt / s < 8) continue;
       const int64_t ctas = ft * nbt * s;
-      const int64_t waves = ceil_div(ctas, sms);
+      int64_t waves = ceil_div(ctas, sms);
+      if (residency && s > 1) {
+        const int64_t w2 = ceil_div(ft * nbt, sk_resident_clusters(bt, s, (int)(kb / s), sms));
+        if (w2 > waves) waves = w2;
+      }
       const double bytes = (double)(kb / s) * (SK_W_BYTES + bt * 128);
       const double cost = waves * (1.0 + bytes / 150e3) + (s > 1 ? 0.6 + bt * 512.0 / 200e3 : 0.0);     // microseconds
       if (cost < best) { best = cost; *bt_out = bt; *s_out = s; }
@@ -320,7 +383,8 @@ extern "C" int vg_skinny_linear(const vg_skinny_linear_args* a, vg_stream_t stre
     VG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   int bt = 64, S = 1;
-  sk_plan(a->B, a->N, a->K, sms, &bt, &S);
+  static const int env_res = getenv("VG_SK_RESIDENCY") ? atoi(getenv("VG_SK_RESIDENCY")) : 1;
+  sk_plan(a->B, a->N, a->K, sms, env_res && a->B > 64, &bt, &S);
   static const int env_bt = getenv("VG_SK_BT") ? atoi(getenv("VG_SK_BT")) : 0;
   static const int env_s = getenv("VG_SK_S") ? atoi(getenv("VG_SK_S")) : 0;
   if (env_bt) bt = env_bt;
@@ -332,26 +396,27 @@ extern "C" int vg_skinny_linear(const vg_skinny_linear_args* a, vg_stream_t stre
   p.FT = (int)ceil_div(a->N, SK_FT);
   p.act = a->act; p.y_f32 = a->y_dtype == VG_F32; p.mask_first = a->mask_before_residual;
   p.ss_in = a->row_ss_in; p.ss_out = a->row_ss_out; p.zero_ss = a->zero_ss; p.inv_k = a->ss_inv_k; p.eps = a->ss_eps;
-  const int stage = SK_W_BYTES + bt * 128;
-  int ns = (200 * 1024) / stage;
-  if (ns > SK_MAX_STAGES) ns = SK_MAX_STAGES;
-  if (ns > p.nkb) ns = p.nkb;
+  int ns;
+  size_t smem;
+  sk_smem(bt, p.nkb, &ns, &smem);
   p.NS = ns;
-  const int ring = ns * stage > bt * SK_FT * 4 ? ns * stage : bt * SK_FT * 4;
-  const size_t smem = 1024 + (size_t)ring + sizeof(SkBars) + 64;
+  static const int env_dbg = getenv("VG_SK_DEBUG") ? atoi(getenv("VG_SK_DEBUG")) : 0;
+  if (env_dbg) {
+    static int printed = 0;
+    if (printed < 64) {
+      ++printed;
+      fprintf(stderr, "[vg_skinny_linear] B=%lld N=%lld K=%lld -> bt=%d S=%d stages=%d smem=%zu resident clusters=%d (of %lld)\n",
+              (long long)a->B, (long long)a->N, (long long)a->K, bt, S, ns, smem,
+              S > 1 ? sk_resident_clusters(bt, S, p.nkb, sms) : sms, (long long)(ceil_div(a->N, SK_FT) * ceil_div(a->B, bt)));
+    }
+  }
   CUtensorMap tmW, tmX;
   int rc = make_tmap_bf16_2d(&tmW, a->w, a->K, a->N, a->ldw, 64, SK_FT);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmX, a->x, a->K, a->B, a->ldx, 64, bt);
   if (rc) return rc;
-  void (*kern)(const CUtensorMap, const CUtensorMap, const SkParams) =
-      bt == 64 ? skinny_linear_kernel<64> : (bt == 128 ? skinny_linear_kernel<128> : skinny_linear_kernel<256>);
-  static bool attr_set[3] = {false, false, false};
-  const int ki = bt == 64 ? 0 : (bt == 128 ? 1 : 2);
-  if (!attr_set[ki]) {
-    VG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[ki] = true;
-  }
+  SkKernel kern = sk_kernel(bt);
+  if (sk_set_smem_attr(bt)) return -2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(p.FT * ceil_div(a->B, bt) * S));
   cfg.blockDim = dim3(SK_THREADS);

@@ -296,13 +296,17 @@ def rmsnorm_residual(x: torch.Tensor, scale: torch.Tensor, eps: float, mask: Opt
 PROFILE_SPIN = 0            # device clock cycles of spin in front of every profiled GEMM (bench.py's instrumented pass)
 SKINNY_LINEAR = os.environ.get("VG_SKINNY_LINEAR", "1") != "0"
 SKINNY_MAX_ROWS = int(os.environ.get("VG_SKINNY_MAX_ROWS", "64"))      # above: gemm_tc's skinny-M plan (profiles/r02_decode.md)
+# up to this many rows the layers with <= 1024 output features (out-projection, W2 of the FFN: long k-range, 8..16 output
+# tiles in the general GEMM) still go to vg_skinny_linear, whose cluster splits the k-range
+SKINNY_MIXED_ROWS = int(os.environ.get("VG_SKINNY_MIXED_ROWS", "256"))
 
 
 def _skinny_ok(x2: torch.Tensor, w: torch.Tensor) -> bool:
     """bf16 linear layers on few rows (one new frame per sequence) whose inputs need no gradient go to vg_skinny_linear
     (autograd.Function.forward runs with grad mode off even in training: the callers test ctx.needs_input_grad)"""
     return (SKINNY_LINEAR and x2.is_cuda and x2.dtype == torch.bfloat16
-            and w.dtype == torch.bfloat16 and x2.shape[0] <= SKINNY_MAX_ROWS and x2.shape[1] % 64 == 0 and w.shape[0] >= 8
+            and w.dtype == torch.bfloat16 and x2.shape[1] % 64 == 0 and w.shape[0] >= 8
+            and (x2.shape[0] <= SKINNY_MAX_ROWS or (x2.shape[0] <= SKINNY_MIXED_ROWS and w.shape[0] <= 1024))
             and x2.stride(0) % 8 == 0 and x2.stride(1) == 1 and w.is_contiguous())
 
 
@@ -433,6 +437,15 @@ class _FFN(torch.autograd.Function):
             h = skinny_linear(x2, w1c, b1.detach().float() if b1 is not None else None, act)
             y = skinny_linear(h, w2c, b2.detach().float() if b2 is not None else None, ACT_NONE,
                               _rows2d(residual) if residual is not None else None, mask_u8)
+            return y.view(x.shape[:-1] + (w2c.shape[0],))
+        if not any(ctx.needs_input_grad) and x2.dtype == torch.bfloat16 and x2.is_cuda:
+            h = gemm(x2, w1c, trans_b=True, bias=b1.detach().float() if b1 is not None else None, act=act)
+            if _skinny_ok(h, w2c):            # SKINNY_MIXED_ROWS: W2's k-range split inside a cluster
+                y = skinny_linear(h, w2c, b2.detach().float() if b2 is not None else None, ACT_NONE,
+                                  _rows2d(residual) if residual is not None else None, mask_u8)
+                return y.view(x.shape[:-1] + (w2c.shape[0],))
+            y = gemm(h, w2c, trans_b=True, bias=b2.detach().float() if b2 is not None else None,
+                     residual=_rows2d(residual) if residual is not None else None, row_mask=mask_u8)
             return y.view(x.shape[:-1] + (w2c.shape[0],))
         pre = torch.empty((M, F), dtype=x2.dtype, device=x.device)
         h = gemm(x2, w1c, trans_b=True, bias=b1.detach().float() if b1 is not None else None, act=act, preact=pre,
