@@ -377,7 +377,7 @@ def decode_bench(model, dev, peaks, batches=(1, 64, 256), prompt=150, gen=500, d
         bytes_step = 408.7e6 + B * 65536 * (mean_tk + 1)
         roof = B * peaks["hbm_gbs"] * 1e9 / bytes_step
         eng = model.__dict__.get("_decode_engines", {}).get(B)
-        path = type(eng[1]).__name__ if (eng and model.use_decode_engine) else "layer-by-layer (tcgen05 GEMM)"
+        path = type(eng[1]).__name__ if (eng and model.use_decode_engine) else "layer-by-layer (tcgen05 GEMM; <= 1024-feature layers on vg_skinny_linear)"
         out[f"B{B}"] = {"frames_per_sec": round(B / (ms / 1e3), 1), "ms_per_step": round(ms, 4),
                         "hbm_roofline_frames_per_sec": round(roof, 1), "frac": round(B / (ms / 1e3) / roof, 4),
                         "achieved_gbs": round(bytes_step / (ms / 1e3) / 1e9, 1), "steps": steps,

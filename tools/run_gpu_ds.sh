@@ -1,4 +1,9 @@
 mkdir -p gpurun_out
-( time timeout 185 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu_all.log 2>&1; grep "passed\|failed\|Error" gpurun_out/pytest_gpu_all.log | head -5
-( timeout 60 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
-timeout 40 python tools/decode_bench.py 128 256 --kind=layerwise 2>/dev/null | cut -c1-120
+timeout 125 python bench.py --no-gpu-reference --no-cpu-baseline --no-shapes --steps 10 > gpurun_out/bench_last.json 2> gpurun_out/bench_last.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_last.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['gpu_launches'])
+for k,v in d['decode'].items():
+    print(k, v.get('ms_per_step'), v.get('frac'), v.get('path', v.get('mode','')))
+PY
